@@ -1,0 +1,70 @@
+"""ctypes binding of libhsd_b200.so (the C-ABI in include/hsd_b200.h).
+
+There is deliberately NO fallback: if the library has not been built, importing
+this module raises, and every wrapper raises RuntimeError on a non-zero return
+code with the library's own message.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_float, c_int32, c_int64, c_void_p, POINTER
+
+from .build import LIB
+
+HEADER_SYMBOLS = [
+    "hsd_version", "hsd_last_error_string", "hsd_ring_signature_degree", "hsd_bfs_rings",
+    "hsd_signature_transpose", "hsd_pairwise_l1", "hsd_ring_signature_values",
+    "hsd_pairwise_w1_merge", "hsd_pairwise_aligned", "hsd_cheb_spmm", "hsd_ring_reduce",
+    "hsd_fp32_peak_probe",
+]
+
+
+class HSDLibraryMissing(ImportError):
+    pass
+
+
+def _load() -> ctypes.CDLL:
+    if not os.path.exists(LIB):
+        raise HSDLibraryMissing(
+            f"{LIB} is missing: build it with `python -m hsd_b200.build` "
+            "(or `python -c 'import __graft_entry__ as g; g.build()'`). "
+            "hsd_b200 has no CPU fallback.")
+    return ctypes.CDLL(LIB)
+
+
+lib = _load()
+
+_P = c_void_p
+lib.hsd_version.restype = c_int32
+lib.hsd_last_error_string.restype = c_char_p
+lib.hsd_ring_signature_degree.argtypes = [_P, _P, c_int32, _P, _P, c_int32, c_int32, c_int32,
+                                          _P, _P, c_int32, _P, c_int64, _P, _P, c_int32, _P, _P]
+lib.hsd_bfs_rings.argtypes = [_P, _P, c_int32, _P, _P, c_int32, c_int32, c_int32, _P, _P, _P]
+lib.hsd_signature_transpose.argtypes = [_P, c_int64, c_int32, c_int32, _P, c_int64, c_int32, _P]
+lib.hsd_pairwise_l1.argtypes = [_P, c_int32, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                _P, c_int64, _P]
+lib.hsd_ring_signature_values.argtypes = [_P, c_int64, _P, _P, _P, _P, c_int32, c_int32, c_int32,
+                                          c_int32, _P, _P]
+lib.hsd_pairwise_w1_merge.argtypes = [_P, _P, _P, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                      c_int32, _P, c_int64, _P, _P]
+lib.hsd_pairwise_aligned.argtypes = [_P, _P, _P, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                     c_int32, c_int32, _P, c_int64, _P]
+lib.hsd_cheb_spmm.argtypes = [_P, _P, c_int32, c_double, _P, c_int32, c_int32, c_int32, c_int32,
+                              c_double, _P, _P, _P]
+lib.hsd_ring_reduce.argtypes = [_P, c_int32, c_int32, c_int32, _P, _P, _P, c_int32, c_int32, _P, _P]
+lib.hsd_fp32_peak_probe.argtypes = [_P, c_int32, POINTER(c_int64), _P]
+for _name in HEADER_SYMBOLS:
+    if _name not in ("hsd_last_error_string",):
+        getattr(lib, _name).restype = c_int32
+
+
+class HSDError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libhsd_b200 error {code}: {msg}")
+        self.code = code
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise HSDError(rc, (lib.hsd_last_error_string() or b"").decode())

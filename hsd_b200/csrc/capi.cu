@@ -1,0 +1,56 @@
+// C-ABI plumbing: error string, version, signature transpose.
+#include <stdarg.h>
+#include <string.h>
+#include "hsd_common.cuh"
+
+namespace hsd {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// sig[r][k] (row-major, ld) -> sigT[k][col0 + r] (ld n_pad); 32x32 tiles through shared memory
+__global__ void __launch_bounds__(256)
+signature_transpose_kernel(const float* __restrict__ sig, int64_t sig_ld, int n_rows, int k_used,
+                           float* __restrict__ sigT, int64_t n_pad, int col0) {
+    __shared__ float tile[32][33];
+    const int r0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int r = r0 + ty + q * 8, k = k0 + tx;
+        tile[ty + q * 8][tx] = (r < n_rows && k < k_used) ? sig[(int64_t)r * sig_ld + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int k = k0 + ty + q * 8, r = r0 + tx;
+        if (k < k_used && r < n_rows) sigT[(int64_t)k * n_pad + col0 + r] = tile[tx][ty + q * 8];
+    }
+}
+
+}  // namespace hsd
+
+extern "C" int hsd_version(void) { return 100; }
+
+extern "C" const char* hsd_last_error_string(void) { return hsd::g_err; }
+
+extern "C" int hsd_signature_transpose(const float* sig, int64_t sig_ld, int32_t n_rows,
+                                       int32_t k_used, float* sigT, int64_t n_pad, int32_t col0,
+                                       void* stream) {
+    using namespace hsd;
+    HSD_REQUIRE(sig && sigT, "null pointer");
+    HSD_REQUIRE(n_rows >= 0 && k_used >= 0 && sig_ld >= k_used, "bad sizes");
+    HSD_REQUIRE(col0 >= 0 && col0 + (int64_t)n_rows <= n_pad, "column range exceeds n_pad");
+    if (n_rows == 0 || k_used == 0) return HSD_OK;
+    dim3 grid((n_rows + 31) / 32, (k_used + 31) / 32);
+    signature_transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(sig, sig_ld, n_rows, k_used,
+                                                                      sigT, n_pad, col0);
+    HSD_CUDA_TRY(cudaGetLastError());
+    return HSD_OK;
+}

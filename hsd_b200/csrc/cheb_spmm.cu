@@ -1,0 +1,213 @@
+// K4 — Chebyshev heat-kernel wavelets as a CSR SpMM, and K5 — the ring
+// gather-reduce that turns wavelet columns into MultiHSD embeddings.
+//
+// Reference loops replaced: model/HSD.py:50-59 (pygsp cheby_op applied to one
+// unit impulse at a time: N x order SpMVs) and model/multiscale_HSD.py:45-61
+// (Python gather of Psi[i, ring_h(i)] -> [sum, mean]).
+//
+// The recurrence runs on a block of impulse columns at once, node-major
+// ([node][column], columns contiguous) so neighbour rows are read with
+// coalesced 128-byte requests; all scales share T_k and are accumulated in the
+// same pass.  FP64 throughout: the SpMM is bandwidth-bound and FP32 cannot hold
+// 1e-5 relative on coefficients that span nine orders of magnitude.
+#include "hsd_common.cuh"
+
+namespace hsd {
+
+constexpr int MAX_SCALES = 8;
+
+struct ChebArgs {
+    const int32_t* rowptr;
+    const int32_t* col;
+    int n_nodes, n_cols, col0;
+    int k, order, n_scales;
+    double a;          // lmax / 2
+    double threshold;
+    double ck[MAX_SCALES];   // c_{s,k}
+    double c0[MAX_SCALES];   // c_{s,0} (used at k == 1)
+    const double* t_prev;    // T_{k-1}
+    const double* t_prev2;   // T_{k-2} (k >= 2)
+    double* t_new;
+    double* out;             // [n_scales][n_nodes][n_cols]
+};
+
+__global__ void cheb_init_kernel(double* t0, int n_nodes, int n_cols, int col0) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)n_nodes * n_cols) return;
+    const int v = (int)(idx / n_cols), c = (int)(idx - (int64_t)v * n_cols);
+    t0[idx] = (v == col0 + c) ? 1.0 : 0.0;
+}
+
+// one thread per (node v, column c); blockDim.x spans columns, blockDim.y nodes
+__global__ void __launch_bounds__(256) cheb_step_kernel(const ChebArgs p) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = blockIdx.y * blockDim.y + threadIdx.y;
+    if (c >= p.n_cols || v >= p.n_nodes) return;
+    const int e0 = __ldg(p.rowptr + v), e1 = __ldg(p.rowptr + v + 1);
+    double nb = 0.0;
+    int deg = 0;
+    for (int e = e0; e < e1; ++e) {
+        const int u = __ldg(p.col + e);
+        if (u == v) continue;  // nx.laplacian_matrix: a self-loop cancels out of D - A
+        nb += p.t_prev[(int64_t)u * p.n_cols + c];
+        ++deg;
+    }
+    const int64_t idx = (int64_t)v * p.n_cols + c;
+    const double tp = p.t_prev[idx];
+    const double lx = ((double)deg - p.a) * tp - nb;  // ((L - a I) T_{k-1})[v][c]
+    double t;
+    if (p.k == 1) t = lx / p.a;
+    else t = (2.0 / p.a) * lx - p.t_prev2[idx];
+    p.t_new[idx] = t;
+    const int64_t plane = (int64_t)p.n_nodes * p.n_cols;
+    const bool last = (p.k == p.order);
+#pragma unroll
+    for (int s = 0; s < MAX_SCALES; ++s) {
+        if (s >= p.n_scales) break;
+        double r = (p.k == 1) ? 0.5 * p.c0[s] * tp : p.out[s * plane + idx];
+        r += p.ck[s] * t;
+        if (last) r = (r > p.threshold) ? r : 0.0;  // model/HSD.py:65
+        p.out[s * plane + idx] = r;
+    }
+}
+
+// order == 0 degenerate case: R = c0/2 * E (+ threshold)
+__global__ void cheb_order0_kernel(const double* t0, double* out, int64_t n, double c0, double thr) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const double r = 0.5 * c0 * t0[idx];
+    out[idx] = (r > thr) ? r : 0.0;
+}
+
+// ---------------- K5 ----------------
+constexpr int RR_MAX_HOPS1 = 8;
+
+__global__ void __launch_bounds__(128)
+ring_reduce_kernel(const double* __restrict__ psiT, int n_nodes, int n_cols,
+                   const uint32_t* __restrict__ bitmaps, const int32_t* __restrict__ orig_of,
+                   int hops1, int n_words, int col0, int v_chunk, int n_scales,
+                   double* __restrict__ emb) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = blockIdx.z;
+    if (c >= n_cols) return;
+    const int v_lo = blockIdx.y * v_chunk, v_hi = min(v_lo + v_chunk, n_nodes);  // multiples of 32
+    const uint32_t* bm = bitmaps + (int64_t)(col0 + c) * hops1 * n_words;
+    const double* ps = psiT + (int64_t)s * n_nodes * n_cols + c;
+    double acc[RR_MAX_HOPS1];
+#pragma unroll
+    for (int h = 0; h < RR_MAX_HOPS1; ++h) acc[h] = 0.0;
+    for (int w = v_lo >> 5; w < (v_hi + 31) >> 5; ++w) {
+        uint32_t wh[RR_MAX_HOPS1];
+        uint32_t any = 0;
+#pragma unroll
+        for (int h = 0; h < RR_MAX_HOPS1; ++h) {
+            wh[h] = (h < hops1) ? bm[(int64_t)h * n_words + w] : 0u;
+            any |= wh[h];
+        }
+        // every thread walks the same 32 node slots so psiT reads stay coalesced across c
+        const int nv = min(32, n_nodes - (w << 5));
+        for (int b = 0; b < nv; ++b) {
+            const int vid = (w << 5) + b;
+            const int vrow = orig_of ? __ldg(orig_of + vid) : vid;
+            const double x = ps[(int64_t)vrow * n_cols];
+            const uint32_t m = 1u << b;
+            if (any & m) {
+#pragma unroll
+                for (int h = 0; h < RR_MAX_HOPS1; ++h)
+                    if (wh[h] & m) acc[h] += x;
+            }
+        }
+    }
+    double* dst = emb + (((int64_t)(col0 + c) * n_scales + s) * hops1) * 2;
+#pragma unroll
+    for (int h = 0; h < RR_MAX_HOPS1; ++h)
+        if (h < hops1 && acc[h] != 0.0) atomicAdd(dst + 2 * h, acc[h]);
+}
+
+__global__ void ring_mean_kernel(double* emb, const int32_t* __restrict__ sizes, int n_cols,
+                                 int col0, int n_scales, int hops1) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int total = n_cols * n_scales * hops1;
+    if (idx >= total) return;
+    const int h = idx % hops1;
+    const int c = idx / (hops1 * n_scales);
+    const int s = (idx / hops1) % n_scales;
+    const int n = sizes[(int64_t)(col0 + c) * hops1 + h];
+    double* e = emb + (((int64_t)(col0 + c) * n_scales + s) * hops1 + h) * 2;
+    if (n > 0) e[1] = e[0] / (double)n;
+    else { e[0] = 0.0; e[1] = 0.0; }
+}
+
+}  // namespace hsd
+
+extern "C" int hsd_cheb_spmm(const int32_t* rowptr, const int32_t* col, int32_t n_nodes, double lmax,
+                             const double* coeff_host, int32_t n_scales, int32_t order, int32_t col0,
+                             int32_t n_cols, double threshold, double* work, double* out,
+                             void* stream_) {
+    using namespace hsd;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    HSD_REQUIRE(rowptr && col && coeff_host && work && out, "null pointer");
+    HSD_REQUIRE(n_nodes > 0 && n_cols > 0 && col0 >= 0 && col0 + n_cols <= n_nodes, "bad column block");
+    HSD_REQUIRE(n_scales >= 1 && n_scales <= MAX_SCALES, "1..8 scales per call");
+    HSD_REQUIRE(order >= 0 && lmax > 0.0, "bad order / lmax");
+    const int64_t plane = (int64_t)n_nodes * n_cols;
+    double* T[3] = {work, work + plane, work + 2 * plane};
+    {
+        const int64_t nblk = (plane + 255) / 256;
+        HSD_REQUIRE(nblk < (1ll << 31), "column block too large");
+        cheb_init_kernel<<<(unsigned)nblk, 256, 0, stream>>>(T[0], n_nodes, n_cols, col0);
+        HSD_CUDA_TRY(cudaGetLastError());
+        if (order == 0) {
+            for (int s = 0; s < n_scales; ++s)
+                cheb_order0_kernel<<<(unsigned)nblk, 256, 0, stream>>>(T[0], out + s * plane, plane,
+                                                                      coeff_host[s], threshold);
+            HSD_CUDA_TRY(cudaGetLastError());
+            return HSD_OK;
+        }
+    }
+    int bx = 32;
+    while (bx < n_cols && bx < 256) bx <<= 1;
+    const int by = 256 / bx;
+    dim3 block(bx, by), grid((n_cols + bx - 1) / bx, (n_nodes + by - 1) / by);
+    HSD_REQUIRE(grid.y <= 65535u, "too many nodes for one launch dimension");
+    ChebArgs a;
+    a.rowptr = rowptr; a.col = col; a.n_nodes = n_nodes; a.n_cols = n_cols; a.col0 = col0;
+    a.order = order; a.n_scales = n_scales; a.a = lmax / 2.0; a.threshold = threshold; a.out = out;
+    for (int s = 0; s < n_scales; ++s) a.c0[s] = coeff_host[(int64_t)s * (order + 1)];
+    for (int k = 1; k <= order; ++k) {
+        a.k = k;
+        for (int s = 0; s < n_scales; ++s) a.ck[s] = coeff_host[(int64_t)s * (order + 1) + k];
+        a.t_prev = T[(k - 1) % 3];
+        a.t_prev2 = T[(k + 1) % 3];  // == (k-2) mod 3
+        a.t_new = T[k % 3];
+        cheb_step_kernel<<<grid, block, 0, stream>>>(a);
+    }
+    HSD_CUDA_TRY(cudaGetLastError());
+    return HSD_OK;
+}
+
+extern "C" int hsd_ring_reduce(const double* psiT, int32_t n_scales, int32_t n_nodes, int32_t n_cols,
+                               const uint32_t* ring_bitmaps, const int32_t* ring_sizes,
+                               const int32_t* orig_of, int32_t hops, int32_t col0, double* emb,
+                               void* stream_) {
+    using namespace hsd;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    HSD_REQUIRE(psiT && ring_bitmaps && ring_sizes && emb, "null pointer");
+    HSD_REQUIRE(n_scales >= 1 && n_nodes > 0 && n_cols > 0 && col0 >= 0 && col0 + n_cols <= n_nodes, "bad sizes");
+    HSD_REQUIRE(hops >= 0 && hops + 1 <= RR_MAX_HOPS1, "hops must be <= 7");
+    HSD_REQUIRE(n_scales <= 65535, "too many scales");
+    const int hops1 = hops + 1, n_words = (n_nodes + 31) / 32;
+    // split the node range so the grid has enough CTAs to pull HBM bandwidth
+    int chunks = (148 * 8) / (((n_cols + 127) / 128) * n_scales);
+    chunks = chunks < 1 ? 1 : chunks;
+    int v_chunk = ((n_nodes + chunks - 1) / chunks + 31) / 32 * 32;
+    chunks = (n_nodes + v_chunk - 1) / v_chunk;
+    dim3 grid((n_cols + 127) / 128, chunks, n_scales);
+    ring_reduce_kernel<<<grid, 128, 0, stream>>>(psiT, n_nodes, n_cols, ring_bitmaps, orig_of, hops1,
+                                                 n_words, col0, v_chunk, n_scales, emb);
+    HSD_CUDA_TRY(cudaGetLastError());
+    const int total = n_cols * n_scales * hops1;
+    ring_mean_kernel<<<(total + 255) / 256, 256, 0, stream>>>(emb, ring_sizes, n_cols, col0, n_scales, hops1);
+    HSD_CUDA_TRY(cudaGetLastError());
+    return HSD_OK;
+}

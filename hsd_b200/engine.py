@@ -1,0 +1,212 @@
+"""Device pipeline: CSR -> rings -> signatures -> pairwise distances.
+
+torch is used for device memory, streams and (in sharded.py) torch.distributed;
+every arithmetic step is a hand-written kernel reached through the C-ABI in
+include/hsd_b200.h.  There is no CPU path: all functions here require CUDA
+tensors and raise otherwise.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, lib
+from .graph import CSRGraph
+
+PAIR_TILE = 128
+PAIR_KCHUNK = 16
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("hsd_b200 kernels need CUDA tensors (there is no CPU fallback)")
+    if not t.is_contiguous():
+        raise RuntimeError("hsd_b200 kernels need contiguous tensors")
+    return t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("hsd_b200 requires a CUDA device (B200 / sm_100a); no CPU fallback exists")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def roundup(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+# --------------------------------------------------------------------------
+# device-resident graph
+# --------------------------------------------------------------------------
+@dataclass
+class DeviceGraph:
+    """CSR in degree-ascending order on the device + the shared degree support."""
+    n: int
+    rowptr: torch.Tensor
+    col: torch.Tensor
+    orig_of: torch.Tensor      # int32[N] new id -> original index
+    new_of: torch.Tensor       # int32[N]
+    heavy_begin: int
+    bin_end: torch.Tensor      # int32[B]
+    delta: torch.Tensor        # float32[max(B-1,1)]
+    n_bins: int
+    support: np.ndarray        # host float64[B]
+    include_zero: bool
+
+    @classmethod
+    def upload(cls, g: CSRGraph, include_zero: bool = False, device=None,
+               non_blocking: bool = True) -> "DeviceGraph":
+        dev = device or require_cuda()
+        o = g.degree_order()
+        sup, bin_end, delta = o.support(include_zero)
+        if delta.size == 0:
+            delta = np.zeros(1, dtype=np.float32)
+
+        def up(a):
+            return torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=non_blocking)
+
+        return cls(n=g.n, rowptr=up(o.rowptr), col=up(o.col) if o.col.size else torch.zeros(1, dtype=torch.int32, device=dev),
+                   orig_of=up(o.orig_of), new_of=up(o.new_of), heavy_begin=o.heavy_begin,
+                   bin_end=up(bin_end), delta=up(delta), n_bins=int(sup.size), support=sup,
+                   include_zero=include_zero)
+
+    @property
+    def n_words(self) -> int:
+        return (self.n + 31) // 32
+
+    def k_used(self, hops: int) -> int:
+        """Signature length: hop 0 is one scalar (the source degree), every later hop
+        is the delta-scaled CDF over the B-1 gaps of the shared support."""
+        return 1 + hops * (self.n_bins - 1)
+
+
+# --------------------------------------------------------------------------
+# K1/K2
+# --------------------------------------------------------------------------
+def ring_signature_degree(dg: DeviceGraph, hops: int, rows: Optional[torch.Tensor] = None,
+                          want_sig: bool = True, want_sizes: bool = True,
+                          want_bitmaps: bool = False, empty: str = "raise",
+                          sig_ld: Optional[int] = None):
+    """Run the BFS + degree-CDF kernel for the given sources.
+
+    rows: int32 CUDA tensor of ORIGINAL node indices (default: all nodes, in
+    original order).  Output row r belongs to rows[r].  Returns
+    (sig float32[n, sig_ld] | None, ring_sizes int32[n, hops+1] | None,
+     bitmaps uint32-as-int32[n, hops+1, n_words] | None, status int32[1]).
+    Bitmaps are indexed by degree-order id (map with dg.orig_of)."""
+    if empty not in ("raise", "zero"):
+        raise ValueError("empty must be 'raise' or 'zero'")
+    if empty == "zero" and want_sig and not dg.include_zero:
+        raise ValueError("empty='zero' needs a DeviceGraph uploaded with include_zero=True")
+    dev = dg.rowptr.device
+    if rows is None:
+        src = dg.new_of
+        n_src = dg.n
+    else:
+        rows = rows.to(device=dev, dtype=torch.int64)
+        src = dg.new_of[rows].contiguous()
+        n_src = int(rows.numel())
+    out_rows = torch.arange(n_src, dtype=torch.int32, device=dev)
+    k_used = dg.k_used(hops)
+    ld = int(sig_ld) if sig_ld is not None else roundup(k_used, 4)
+    sig = torch.empty((n_src, ld), dtype=torch.float32, device=dev) if want_sig else None
+    if sig is not None and ld > k_used:
+        sig[:, k_used:].zero_()
+    sizes = torch.empty((n_src, hops + 1), dtype=torch.int32, device=dev) if want_sizes else None
+    bitmaps = (torch.empty((n_src, hops + 1, dg.n_words), dtype=torch.int32, device=dev)
+               if want_bitmaps else None)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    check(lib.hsd_ring_signature_degree(
+        _ptr(dg.rowptr), _ptr(dg.col), dg.n, _ptr(src), _ptr(out_rows), n_src, hops,
+        dg.heavy_begin, _ptr(dg.bin_end), _ptr(dg.delta), dg.n_bins,
+        _ptr(sig), ld, _ptr(sizes), _ptr(bitmaps), 1 if empty == "zero" else 0,
+        _ptr(status), _stream()))
+    return sig, sizes, bitmaps, status
+
+
+# --------------------------------------------------------------------------
+# layout + K3
+# --------------------------------------------------------------------------
+def alloc_signature_table(k_used: int, n: int, device) -> torch.Tensor:
+    """Zeroed K-major table float32[k_pad][n_pad] for the pairwise kernel."""
+    k_pad = roundup(max(k_used, 1), PAIR_KCHUNK)
+    n_pad = roundup(n, 4)
+    return torch.zeros((k_pad, n_pad), dtype=torch.float32, device=device)
+
+
+def signature_transpose(sig: torch.Tensor, k_used: int, sigT: torch.Tensor, col0: int = 0) -> None:
+    check(lib.hsd_signature_transpose(_ptr(sig), sig.stride(0), sig.shape[0], k_used,
+                                      _ptr(sigT), sigT.stride(0), col0, _stream()))
+
+
+def pairwise_l1(sigT: torch.Tensor, n: int, row0: int = 0, n_rows: Optional[int] = None,
+                col0: int = 0, n_cols: Optional[int] = None, symmetric: Optional[bool] = None,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[i-row0, j-col0] = sum_k |sigT[k, i] - sigT[k, j]| (float32)."""
+    n_rows = n - row0 if n_rows is None else n_rows
+    n_cols = n - col0 if n_cols is None else n_cols
+    if symmetric is None:
+        symmetric = (row0 == col0 and n_rows == n_cols)
+    if out is None:
+        out = torch.empty((n_rows, n_cols), dtype=torch.float32, device=sigT.device)
+    if out.shape[0] < n_rows or out.shape[1] < n_cols or out.stride(1) != 1:
+        raise ValueError("out too small or not row-major")
+    check(lib.hsd_pairwise_l1(_ptr(sigT), sigT.shape[0], sigT.stride(0), row0, n_rows, col0, n_cols,
+                              1 if symmetric else 0, out.data_ptr(), out.stride(0), _stream()))
+    return out
+
+
+# --------------------------------------------------------------------------
+# whole degree-mode path on one device
+# --------------------------------------------------------------------------
+class EmptyRingError(ValueError):
+    """Raised where the reference's scipy call would raise
+    ValueError("Distribution can't be empty.") (model/HSD.py:111)."""
+
+
+def degree_distance_device(dg: DeviceGraph, hops: int, empty: str = "raise",
+                           row0: int = 0, n_rows: Optional[int] = None,
+                           out: Optional[torch.Tensor] = None,
+                           check_status: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Full degree-mode HSD on the current device: returns (D float32[n_rows, N], ring_sizes).
+
+    D[i, j] = sum_{h=0..hops} W1(deg over ring_h(i), deg over ring_h(j)) — the
+    loop of model/HSD.py:98-114 with a degree-valued ring signal."""
+    n = dg.n
+    k_used = dg.k_used(hops)
+    sig, sizes, _, status = ring_signature_degree(dg, hops, empty=empty)
+    sigT = alloc_signature_table(k_used, n, sig.device)
+    signature_transpose(sig, k_used, sigT, 0)
+    n_rows = n - row0 if n_rows is None else n_rows
+    full = (row0 == 0 and n_rows == n)
+    D = pairwise_l1(sigT, n, row0, n_rows, 0, n, symmetric=full, out=out)
+    if check_status and empty == "raise" and int(status.item()) & 1:
+        raise EmptyRingError("Distribution can't be empty.")
+    return D, sizes
+
+
+def fp32_issue_peak(iters: int = 20000, reps: int = 3) -> float:
+    """Measured FP32 CUDA-core issue rate in lane-ops/s (FADD sub + |.|-accumulate mix)."""
+    dev = require_cuda()
+    sink = torch.zeros(4, dtype=torch.float32, device=dev)
+    ops = ctypes.c_int64(0)
+    best = 0.0
+    for _ in range(reps + 1):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(lib.hsd_fp32_peak_probe(_ptr(sink), iters, ctypes.byref(ops), _stream()))
+        e1.record()
+        e1.synchronize()
+        best = max(best, ops.value / (e0.elapsed_time(e1) * 1e-3))
+    return best

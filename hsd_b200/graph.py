@@ -1,0 +1,120 @@
+"""Graph ingest: networkx / edge arrays -> CSR, plus the degree-ordered view the
+BFS + degree-CDF kernel needs.
+
+Reference counterpart: HSD.__init__ (model/HSD.py:28-40) builds dense N x N
+``A`` and ``L`` and the node <-> index maps; node index = order of first
+appearance (``list(nx.nodes(graph))``, tools/util.py:11-24).  Dense N x N is
+80 GB at N = 100k, so the adjacency lives as int32 CSR here and ``A`` / ``L``
+are materialised lazily by the model classes only when a caller asks.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Hashable, List, Optional, Sequence
+
+import numpy as np
+
+# nodes with more neighbours than this are expanded one warp per node by the BFS kernel
+HEAVY_DEGREE = 32
+
+
+@dataclass
+class DegreeOrder:
+    """CSR relabelled in degree-ascending order (ties by original index)."""
+    orig_of: np.ndarray      # int32[N]  new id -> original index
+    new_of: np.ndarray       # int32[N]  original index -> new id
+    rowptr: np.ndarray       # int32[N+1]
+    col: np.ndarray          # int32[nnz]
+    heavy_begin: int         # first new id with degree > HEAVY_DEGREE
+    sorted_degree: np.ndarray  # int32[N] degree of new id
+
+    def support(self, include_zero: bool = False):
+        """Shared support of all ring degree distributions.
+
+        Returns (support float64[B], bin_end int32[B], delta float32[B-1]) with
+        bin_end[b] = number of nodes whose degree <= support[b]."""
+        sup = np.unique(self.sorted_degree)
+        if include_zero and (sup.size == 0 or sup[0] != 0):
+            sup = np.concatenate([[0], sup])
+        bin_end = np.searchsorted(self.sorted_degree, sup, side="right").astype(np.int32)
+        delta = np.diff(sup).astype(np.float32)
+        return sup.astype(np.float64), bin_end, delta
+
+
+@dataclass
+class CSRGraph:
+    n: int
+    rowptr: np.ndarray   # int32[N+1]
+    col: np.ndarray      # int32[nnz], sorted within a row
+    nodes: List[Hashable] = field(default_factory=list)
+    _order: Optional[DegreeOrder] = None
+
+    @property
+    def nnz(self) -> int:
+        return int(self.col.shape[0])
+
+    @property
+    def degree(self) -> np.ndarray:
+        return np.diff(self.rowptr).astype(np.int32)
+
+    @classmethod
+    def from_edges(cls, n: int, edges: np.ndarray, nodes: Sequence[Hashable] | None = None) -> "CSRGraph":
+        """Undirected simple graph from an (E, 2) index array (each edge once, any
+        orientation; duplicates and both orientations are tolerated)."""
+        edges = np.asarray(edges, dtype=np.int64).reshape(-1, 2)
+        if edges.size and (edges.min() < 0 or edges.max() >= n):
+            raise ValueError("edge endpoint out of range")
+        u = np.concatenate([edges[:, 0], edges[:, 1]])
+        v = np.concatenate([edges[:, 1], edges[:, 0]])
+        key = np.unique(u * n + v)          # dedupe (also collapses a self-loop's two copies)
+        rows = (key // n).astype(np.int64)
+        cols = (key % n).astype(np.int32)   # sorted by (row, col) already
+        rowptr = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(np.bincount(rows, minlength=n), out=rowptr[1:])
+        if rowptr[-1] >= 2**31:
+            raise ValueError("graph too large for int32 CSR")
+        return cls(n=n, rowptr=rowptr.astype(np.int32), col=cols,
+                   nodes=list(nodes) if nodes is not None else list(range(n)))
+
+    @classmethod
+    def from_networkx(cls, graph) -> "CSRGraph":
+        nodes = list(graph.nodes())
+        idx = {v: i for i, v in enumerate(nodes)}
+        e = np.fromiter((idx[x] for uv in graph.edges() for x in uv), dtype=np.int64)
+        return cls.from_edges(len(nodes), e.reshape(-1, 2), nodes)
+
+    def with_edges_added(self, new_edges: np.ndarray) -> "CSRGraph":
+        """A new CSRGraph with extra undirected edges (index pairs)."""
+        rows = np.repeat(np.arange(self.n, dtype=np.int64), np.diff(self.rowptr))
+        old = np.stack([rows, self.col.astype(np.int64)], axis=1)
+        return CSRGraph.from_edges(self.n, np.concatenate([old, np.asarray(new_edges, dtype=np.int64)]),
+                                   self.nodes)
+
+    def degree_order(self) -> DegreeOrder:
+        if self._order is None:
+            deg = self.degree
+            orig_of = np.argsort(deg, kind="stable").astype(np.int32)
+            new_of = np.empty(self.n, dtype=np.int32)
+            new_of[orig_of] = np.arange(self.n, dtype=np.int32)
+            rows = np.repeat(np.arange(self.n, dtype=np.int64), deg)
+            key = np.sort(new_of[rows].astype(np.int64) * self.n + new_of[self.col])
+            sdeg = deg[orig_of]
+            rowptr = np.zeros(self.n + 1, dtype=np.int32)
+            np.cumsum(sdeg, out=rowptr[1:])
+            self._order = DegreeOrder(
+                orig_of=orig_of, new_of=new_of, rowptr=rowptr,
+                col=(key % self.n).astype(np.int32),
+                heavy_begin=int(np.searchsorted(sdeg, HEAVY_DEGREE, side="right")),
+                sorted_degree=sdeg.astype(np.int32))
+        return self._order
+
+    def neighbors(self, i: int) -> np.ndarray:
+        return self.col[self.rowptr[i]:self.rowptr[i + 1]]
+
+
+def powerlaw_graph(n: int, m: int = 5, seed: int = 0) -> CSRGraph:
+    """The synthetic inputs BASELINE.json names: networkx.barabasi_albert_graph(n, m, seed)."""
+    import networkx as nx
+    g = nx.barabasi_albert_graph(n, m, seed=seed)
+    e = np.array(g.edges(), dtype=np.int64)
+    return CSRGraph.from_edges(n, e, list(range(n)))

@@ -1,0 +1,182 @@
+/*
+ * hsd_b200.h — C-ABI of the B200-native HSD structural-distance hot path.
+ *
+ * The reference (Sngunfei/HSD) is pure Python and has no FFI of its own; the
+ * boundary it exposes is the Python class API of model/HSD.py,
+ * model/multiscale_HSD.py, model/dynamic_HSD.py and tools/hierarchy.py.  The
+ * entry points below are what a ctypes binding behind those classes calls
+ * (see INTEGRATION.md for the binding stub).  Each one cites the reference
+ * loop (file:line under the reference tree) it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless the name
+ *     ends in `_host`; no hidden allocation, no hidden synchronisation;
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued on it and
+ *     the call returns immediately;
+ *   - return value: 0 = HSD_OK, negative = error (hsd_last_error_string());
+ *   - node ids are int32; the CSR handed to the BFS entry points must be in
+ *     *degree-ascending node order* (ties by original id).  That order is what
+ *     lets the per-ring degree CDF be a prefix-popcount over the ring bitmap
+ *     instead of a histogram with atomics.
+ */
+#ifndef HSD_B200_H
+#define HSD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HSD_OK                 0
+#define HSD_ERR_INVALID       -1   /* bad argument */
+#define HSD_ERR_CUDA          -2   /* a CUDA runtime/driver call failed */
+#define HSD_ERR_UNSUPPORTED   -3   /* size outside what the kernels handle */
+#define HSD_ERR_NO_DEVICE     -4   /* no sm_100 device / driver entry point */
+
+#define HSD_PAIR_TILE        128   /* pairwise kernel tile edge (nodes) */
+#define HSD_PAIR_KCHUNK       16   /* pairwise kernel K chunk (signature rows) */
+
+int         hsd_version(void);
+const char* hsd_last_error_string(void);
+
+/* ---- K1/K2: k-hop rings + per-ring degree CDF ------------------------------
+ * Replaces tools/hierarchy.py:16-38 (get_hierarchical_representation /
+ * get_node_hierarchical_structure: level-synchronous BFS, rings kept as sets)
+ * and, in degree mode, the per-ring sort inside
+ * scipy.stats.wasserstein_distance as called from model/HSD.py:103-112.
+ *
+ * One CTA per source.  visited / frontier / next-frontier are N-bit bitmaps in
+ * shared memory.  For hop h = 1..hops the ring bitmap is turned into
+ *   sig[row][1 + (h-1)*(n_bins-1) + b] = CDF_h(support[b]) * (support[b+1]-support[b])
+ * for b = 0..n_bins-2, and sig[row][0] = degree(source) (the hop-0 ring is the
+ * source alone, so its W1 term is |deg_i - deg_j|).  L1 distance between two
+ * such rows == sum over hops of the 1-D Wasserstein-1 distance between the
+ * degree multisets of the rings.
+ *
+ *   rowptr[n_nodes+1], col[nnz]   CSR, degree-ascending node order
+ *   src_nodes[n_src]              sources (ids in that order)
+ *   out_rows[n_src]               row of sig / ring_sizes / ring_bitmaps each source writes
+ *   heavy_begin                   first node id handled warp-cooperatively (degree > threshold)
+ *   bin_end[n_bins]               # nodes with degree <= support[b]  (== first id of bin b+1)
+ *   delta[n_bins-1]               support[b+1]-support[b]
+ *   sig (nullable)                float[rows][sig_ld], sig_ld >= 1 + hops*(n_bins-1)
+ *   ring_sizes (nullable)         int32[rows][hops+1]
+ *   ring_bitmaps (nullable)       uint32[rows][hops+1][ceil(n_nodes/32)]
+ *   empty_as_zero                 0: an empty ring sets *status |= 1 (caller raises, like scipy);
+ *                                 1: an empty ring is the point mass at 0 (tools/metrics.py:18-36 padding)
+ *   status                        int32[1], OR-ed flags, caller zeroes it
+ */
+int hsd_ring_signature_degree(const int32_t* rowptr, const int32_t* col, int32_t n_nodes,
+                              const int32_t* src_nodes, const int32_t* out_rows, int32_t n_src,
+                              int32_t hops, int32_t heavy_begin,
+                              const int32_t* bin_end, const float* delta, int32_t n_bins,
+                              float* sig, int64_t sig_ld,
+                              int32_t* ring_sizes, uint32_t* ring_bitmaps,
+                              int32_t empty_as_zero, int32_t* status, void* stream);
+
+/* Rings only (tools/hierarchy.py:25-38, model/HSD.py:87-94 ring sizes). */
+int hsd_bfs_rings(const int32_t* rowptr, const int32_t* col, int32_t n_nodes,
+                  const int32_t* src_nodes, const int32_t* out_rows, int32_t n_src,
+                  int32_t hops, int32_t heavy_begin,
+                  int32_t* ring_sizes, uint32_t* ring_bitmaps, void* stream);
+
+/* ---- layout: row-major signatures -> K-major table for the pairwise kernel --
+ * sig[n_rows][sig_ld] (first k_used columns) -> sigT[k_pad][n_pad] at column
+ * offset col0; rows k_used..k_pad-1 and columns beyond the data must be zero
+ * (caller memsets sigT once). */
+int hsd_signature_transpose(const float* sig, int64_t sig_ld, int32_t n_rows, int32_t k_used,
+                            float* sigT, int64_t n_pad, int32_t col0, void* stream);
+
+/* ---- K3: pairwise L1 over the K-major signature table ----------------------
+ * Replaces the O(N^2 (H+1)) scipy loop model/HSD.py:103-112 (and :144-159).
+ *   out[(i-row0)*ld_out + (j-col0)] = sum_k |sigT[k][i] - sigT[k][j]|
+ * for i in [row0,row0+n_rows), j in [col0,col0+n_cols).
+ * symmetric != 0 requires the two ranges to be equal; only tiles on or above
+ * the diagonal are computed and each is also stored mirrored (the reference
+ * fills dist_mat[i,j] = dist_mat[j,i] the same way, model/HSD.py:112).
+ * sigT: float[k_pad][n_pad], k_pad % HSD_PAIR_KCHUNK == 0, n_pad % 4 == 0,
+ * base 16-byte aligned. Tiles are staged by TMA (cp.async.bulk.tensor.2d). */
+int hsd_pairwise_l1(const float* sigT, int32_t k_pad, int64_t n_pad,
+                    int32_t row0, int32_t n_rows, int32_t col0, int32_t n_cols,
+                    int32_t symmetric, float* out, int64_t ld_out, void* stream);
+
+/* ---- K2 (value mode): ring gather + sort ----------------------------------
+ * Replaces model/HSD.py:71-83 (get_hierarchical_coeffcients) plus the argsort
+ * inside scipy's _cdf_distance.  For each (row r, hop h) gathers
+ * psi[r*psi_ld + orig_of[j]] for every j set in ring_bitmaps[r][h] and writes
+ * them ascending at vals[offsets[r*(hops+1)+h] ...].  offsets = exclusive scan
+ * of ring_sizes (int64).  psi row r must be the wavelet row of the source that
+ * wrote out_row r.  orig_of may be NULL (bitmaps already in psi's column order).
+ * max_ring_size (host-known, from ring_sizes) sizes the in-shared-memory bitonic
+ * sort; rings above 16384 members return HSD_ERR_UNSUPPORTED. */
+int hsd_ring_signature_values(const double* psi, int64_t psi_ld,
+                              const uint32_t* ring_bitmaps, const int32_t* ring_sizes,
+                              const int64_t* offsets, const int32_t* orig_of,
+                              int32_t n_rows, int32_t hops, int32_t n_nodes,
+                              int32_t max_ring_size, double* vals, void* stream);
+
+/* ---- K3 (value mode): exact ragged W1 by two-pointer merge, FP64 ------------
+ * Replaces scipy.stats.wasserstein_distance as called at model/HSD.py:111 on
+ * ragged multisets:  out[i*ld+j] = out[j*ld+i] = sum_h W1(vals_i_h, vals_j_h),
+ * h in [hop_begin, hop_end).  Rows i in [row0,row0+n_rows) against all j > i
+ * (j < n_total); diagonal written as 0. An empty ring sets *status |= 1. */
+int hsd_pairwise_w1_merge(const double* vals, const int64_t* offsets, const int32_t* ring_sizes,
+                          int32_t n_total, int32_t hops, int32_t hop_begin, int32_t hop_end,
+                          int32_t row0, int32_t n_rows,
+                          double* out, int64_t ld_out, int32_t* status, void* stream);
+
+/* ---- K3 (aligned mode, tools/metrics.py:18-36,151-192) ----------------------
+ * The reference's second distance path pads the shorter multiset with zeros,
+ * sorts, and calls scipy on equal-length arrays, i.e.
+ *   d = (1/L) * sum_k |p_desc[k] - q_desc[k]|,  L = max(n_p, n_q), 0 when both empty.
+ * Same ragged ascending `vals` as above. metric: 0 = 'wasserstein', 1 = 'hellinger'
+ * (tools/metrics.py:117-138 on the same aligned ascending arrays). */
+int hsd_pairwise_aligned(const double* vals, const int64_t* offsets, const int32_t* ring_sizes,
+                         int32_t n_total, int32_t hops, int32_t hop_begin, int32_t hop_end,
+                         int32_t metric, int32_t row0, int32_t n_rows,
+                         double* out, int64_t ld_out, void* stream);
+
+/* ---- K4: Chebyshev heat-kernel wavelets as CSR SpMM -------------------------
+ * Replaces pygsp cheby_op as driven one impulse at a time by model/HSD.py:50-59
+ * (and model/GraphWave.py:31-39).  Computes, for a block of n_cols impulse
+ * columns [col0, col0+n_cols) and n_scales coefficient sets,
+ *   R_s = 1/2 c_{s,0} T_0 + sum_{k=1..order} c_{s,k} T_k,
+ *   T_0 = E, T_1 = (L E - a E)/a, T_k = (2/a)(L - a I) T_{k-1} - T_{k-2},  a = lmax/2,
+ * with L = D - A taken from the CSR (original node order, unit weights), then
+ * the reference threshold x > thr ? x : 0 (model/HSD.py:65).
+ *   coeff_host  HOST double[n_scales][order+1] (copied into the launch arguments)
+ *   work     double[3][n_nodes][n_cols]   (T ring buffer)
+ *   out      double[n_scales][n_nodes][n_cols]; out[s][v][c] = Psi_s[col0+c][v] (= Psi_s[v][col0+c], symmetric)
+ */
+int hsd_cheb_spmm(const int32_t* rowptr, const int32_t* col, int32_t n_nodes,
+                  double lmax, const double* coeff_host, int32_t n_scales, int32_t order,
+                  int32_t col0, int32_t n_cols, double threshold,
+                  double* work, double* out, void* stream);
+
+/* ---- K5: ring gather-reduce for MultiHSD embeddings -------------------------
+ * Replaces model/multiscale_HSD.py:45-61 (get_triple) / :64-73 (get_layer_sum):
+ * emb[col0+c][s][h][0..1] = [sum, mean] of psiT[s][v][c] over v in ring_h(col0+c);
+ * empty ring -> [0, 0].  psiT is the output layout of hsd_cheb_spmm
+ * (double[n_scales][n_nodes][n_cols]).  ring_bitmaps / ring_sizes rows are
+ * indexed by the source's ORIGINAL index; bitmap bits are original ids when
+ * orig_of == NULL, degree-order ids (mapped through orig_of) otherwise.
+ *   emb  double[n_nodes][n_scales][hops+1][2]; rows col0..col0+n_cols-1 must be
+ *        zero on entry (sums are accumulated with FP64 atomics, then the mean
+ *        is filled in).  hops <= 7. */
+int hsd_ring_reduce(const double* psiT, int32_t n_scales, int32_t n_nodes, int32_t n_cols,
+                    const uint32_t* ring_bitmaps, const int32_t* ring_sizes,
+                    const int32_t* orig_of, int32_t hops, int32_t col0, double* emb, void* stream);
+
+/* ---- measurement helper: FP32 CUDA-core issue peak ---------------------------
+ * Runs a register-only FADD kernel (same sub + |.|-accumulate instruction mix as
+ * the pairwise inner loop, no memory) and returns lane-ops in *lane_ops; the
+ * caller times it with events on `stream`.  Used by bench.py for the live
+ * roofline denominator. */
+int hsd_fp32_peak_probe(float* sink, int32_t iters, int64_t* lane_ops_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HSD_B200_H */

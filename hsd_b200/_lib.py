@@ -15,7 +15,7 @@ from .build import LIB
 HEADER_SYMBOLS = [
     "hsd_version", "hsd_last_error_string", "hsd_ring_signature_degree", "hsd_bfs_rings",
     "hsd_signature_transpose", "hsd_pairwise_l1", "hsd_ring_signature_values",
-    "hsd_pairwise_w1_merge", "hsd_pairwise_aligned", "hsd_cheb_spmm", "hsd_ring_reduce",
+    "hsd_pairwise_w1_merge", "hsd_pairwise_aligned", "hsd_pairwise_worker", "hsd_cheb_spmm", "hsd_ring_reduce",
     "hsd_fp32_peak_probe",
 ]
 
@@ -34,6 +34,9 @@ def _load() -> ctypes.CDLL:
 
 
 lib = _load()
+_missing = [s for s in HEADER_SYMBOLS if not hasattr(lib, s)]
+if _missing:
+    raise HSDLibraryMissing(f"{LIB} is stale (missing {_missing}); rebuild it with `python hsd_b200/build.py --force`")
 
 _P = c_void_p
 lib.hsd_version.restype = c_int32
@@ -50,6 +53,8 @@ lib.hsd_pairwise_w1_merge.argtypes = [_P, _P, _P, c_int32, c_int32, c_int32, c_i
                                       c_int32, _P, c_int64, _P, _P]
 lib.hsd_pairwise_aligned.argtypes = [_P, _P, _P, c_int32, c_int32, c_int32, c_int32, c_int32,
                                      c_int32, c_int32, _P, c_int64, _P]
+lib.hsd_pairwise_worker.argtypes = [_P, _P, _P, _P, _P, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                    c_int32, _P, c_int64, _P]
 lib.hsd_cheb_spmm.argtypes = [_P, _P, c_int32, c_double, _P, c_int32, c_int32, c_int32, c_int32,
                               c_double, _P, _P, _P]
 lib.hsd_ring_reduce.argtypes = [_P, c_int32, c_int32, c_int32, _P, _P, _P, c_int32, c_int32, _P, _P]

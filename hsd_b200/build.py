@@ -1,6 +1,6 @@
 """In-tree build of the C-ABI library (nvcc, sm_100a only).
 
-`python -m hsd_b200.build` or `__graft_entry__.build()` compiles every
+`python hsd_b200/build.py` or `__graft_entry__.build()` compiles every
 `csrc/*.cu` into `hsd_b200/libhsd_b200.so`.  The .so is git-ignored but travels
 to the GPU box with the repo snapshot.
 """

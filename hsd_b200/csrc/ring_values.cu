@@ -160,6 +160,73 @@ pairwise_aligned_kernel(const double* __restrict__ vals, const int64_t* __restri
     out[(int64_t)j * ld + i] = d;
 }
 
+
+// ---- K3w: the reference's row worker exactly as written (model/HSD.py:140-161) ----
+// d(i, j) = sum_{h < hop_end} aligned(Psi[i, ring_h(i)], Psi[i, ring_h(j)]) — BOTH signals
+// are read from wavelet row i (the reference indexes q with startIndex, :155).
+// order[i][t] = node with the t-th smallest Psi[i, .]; walking it while testing ring
+// membership yields both ascending sequences without any per-pair sort.
+struct RingStream {
+    const double* sv; const int* ord; const int32_t* bit_of; const uint32_t* bm;
+    int n_nodes, t, zeros;
+    double head; bool has;
+    __device__ RingStream(const double* sv_, const int* ord_, const int32_t* bit_of_, const uint32_t* bm_,
+                          int n_nodes_, int n_members, int L)
+        : sv(sv_), ord(ord_), bit_of(bit_of_), bm(bm_), n_nodes(n_nodes_), t(0), zeros(L - n_members),
+          head(0.0), has(false) { advance(); }
+    __device__ void advance() {
+        has = false;
+        while (t < n_nodes) {
+            const int node = ord[t];
+            const int b = bit_of ? bit_of[node] : node;
+            if ((bm[b >> 5] >> (b & 31)) & 1u) { head = sv[t]; has = true; ++t; return; }
+            ++t;
+        }
+    }
+    __device__ double next() {  // ascending zero-padded sequence (tools/metrics.py:27-30)
+        if (has && (head < 0.0 || zeros == 0)) { const double x = head; advance(); return x; }
+        --zeros;
+        return 0.0;
+    }
+};
+
+__global__ void __launch_bounds__(128)
+pairwise_worker_kernel(const double* __restrict__ sorted_vals, const int32_t* __restrict__ order,
+                       const uint32_t* __restrict__ bitmaps, const int32_t* __restrict__ sizes,
+                       const int32_t* __restrict__ bit_of, int n, int hops1, int n_words, int hop_end,
+                       int metric, int row0, double* __restrict__ out, int64_t ld) {
+    const int i = row0 + blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    if (j <= i) { out[(int64_t)i * ld + j] = 0.0; return; }  // the worker leaves columns <= startIndex at 0
+    const double* sv = sorted_vals + (int64_t)i * n;
+    const int* ord = order + (int64_t)i * n;
+    double d = 0.0;
+    for (int h = 0; h < hop_end; ++h) {
+        const int ni = sizes[i * hops1 + h], nj = sizes[j * hops1 + h];
+        const int L = max(ni, nj);
+        if (L == 0) continue;
+        RingStream P(sv, ord, bit_of, bitmaps + ((int64_t)i * hops1 + h) * n_words, n, ni, L);
+        RingStream Q(sv, ord, bit_of, bitmaps + ((int64_t)j * hops1 + h) * n_words, n, nj, L);
+        if (metric == 0) {
+            double s = 0.0;
+            for (int k = 0; k < L; ++k) s += fabs(P.next() - Q.next());
+            d += s / (double)L;
+        } else {
+            double bc = 0.0;
+            for (int k = 0; k < L; ++k) {
+                const double px = P.next(), qx = Q.next();
+                if (px < 0.0 || qx < 0.0) continue;
+                bc += sqrt(fmax(px * qx, 0.0));
+            }
+            if (fabs(bc) <= 1e-6) bc = 0.0;
+            else if (fabs(bc - 1.0) <= fmax(1e-9 * fmax(fabs(bc), 1.0), 1e-6)) bc = 1.0;
+            d += sqrt(fmax(1.0 - bc, 0.0));
+        }
+    }
+    out[(int64_t)i * ld + j] = d;
+}
+
 }  // namespace hsd
 
 extern "C" int hsd_ring_signature_values(const double* psi, int64_t psi_ld,
@@ -221,6 +288,26 @@ extern "C" int hsd_pairwise_aligned(const double* vals, const int64_t* offsets,
     dim3 grid((n_total + 255) / 256, n_rows);
     pairwise_aligned_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
         vals, offsets, ring_sizes, n_total, hops + 1, hop_begin, hop_end, metric, row0, n_rows, out, ld_out);
+    HSD_CUDA_TRY(cudaGetLastError());
+    return HSD_OK;
+}
+
+extern "C" int hsd_pairwise_worker(const double* sorted_vals, const int32_t* order,
+                                   const uint32_t* ring_bitmaps, const int32_t* ring_sizes,
+                                   const int32_t* bit_of, int32_t n_nodes, int32_t hops,
+                                   int32_t hop_end, int32_t metric, int32_t row0, int32_t n_rows,
+                                   double* out, int64_t ld_out, void* stream) {
+    using namespace hsd;
+    HSD_REQUIRE(sorted_vals && order && ring_bitmaps && ring_sizes && out, "null pointer");
+    HSD_REQUIRE(metric == 0 || metric == 1, "metric must be 0 (wasserstein) or 1 (hellinger)");
+    HSD_REQUIRE(n_nodes > 0 && hops >= 0 && hop_end >= 0 && hop_end <= hops + 1, "bad hop range");
+    HSD_REQUIRE(row0 >= 0 && n_rows >= 0 && row0 + n_rows <= n_nodes && ld_out >= n_nodes, "bad row range");
+    if (n_rows == 0) return HSD_OK;
+    HSD_REQUIRE(n_rows <= 65535, "at most 65535 rows per call");
+    dim3 grid((n_nodes + 127) / 128, n_rows);
+    pairwise_worker_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(
+        sorted_vals, order, ring_bitmaps, ring_sizes, bit_of, n_nodes, hops + 1, (n_nodes + 31) / 32,
+        hop_end, metric, row0, out, ld_out);
     HSD_CUDA_TRY(cudaGetLastError());
     return HSD_OK;
 }

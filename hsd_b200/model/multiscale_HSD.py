@@ -1,0 +1,130 @@
+"""Drop-in for ``model/multiscale_HSD.py`` (class MultiHSD, :15-119).
+
+embed / parallel_embed run the Chebyshev SpMM kernel on blocks of impulse columns
+for up to 8 scales at a time and reduce each block straight into the per-node
+[sum, mean] ring statistics (hsd_cheb_spmm -> hsd_ring_reduce); the dense N x N
+wavelet matrix the reference ships through a multiprocessing pipe per scale
+(:79-81) is never materialised.
+"""
+from __future__ import annotations
+
+from collections import defaultdict
+
+import networkx as nx
+import numpy as np
+import torch
+
+from .. import engine, rings as _rings, wavelets as _wav
+from .._lib import check, lib
+from .HSD import HSD
+
+
+class MultiHSD(HSD):
+
+    def __init__(self, graph: nx.Graph, graphName: str, hop: int, n_scales: int, metric="euclidean",
+                 signal="wavelet", device=None):
+        super(MultiHSD, self).__init__(graph, graphName, 0, hop, metric, signal=signal, device=device)
+        self.n_scales = n_scales
+        self.scales = None
+        self.embeddings = None
+        self.init()
+
+    def init(self):
+        """model/multiscale_HSD.py:26-31: scales from the (estimated) largest Laplacian
+        eigenvalue; rings from a .layers file when one is configured, else the BFS kernel."""
+        if self.signal == "degree":
+            self.scales = np.zeros(1)   # the degree signal has no scale axis
+        else:
+            if self.lmax is None:
+                self.lmax = _wav.estimate_lmax(self.csr)
+            self.scales = np.exp(np.linspace(np.log(0.01), np.log(self.lmax * 1.25), self.n_scales))
+        super(MultiHSD, self).init()
+
+    # ---- batched device path ----
+    def embed_device(self, approx=True, stat="triple") -> torch.Tensor:
+        """emb[N, n_scales, hop+1, 2] float64 = [sum, mean] of Psi_s[i, ring_h(i)]."""
+        n, hops = self.n_node, self.hop
+        rings = self._rings()
+        scales = [float(s) for s in self.scales]
+        dev = self._device()
+        emb = torch.zeros((n, len(scales), hops + 1, 2), dtype=torch.float64, device=dev)
+        sizes = rings.sizes.contiguous()
+        thr = self.THRESHOLD_COEFF * 1.0 / n
+        if approx:
+            csr = self._device_csr()
+            if self.lmax is None:
+                self.lmax = _wav.estimate_lmax(self.csr)
+            for s0 in range(0, len(scales), 8):
+                sc = scales[s0:s0 + 8]
+                coeffs = np.stack([_wav.cheby_coefficients(s, self.lmax, self.CHEB_ORDER) for s in sc])
+                cb = _wav.column_block(n, len(sc))
+                work = torch.empty((3, n, cb), dtype=torch.float64, device=dev)
+                out = torch.empty((len(sc), n, cb), dtype=torch.float64, device=dev)
+                part = torch.zeros((n, len(sc), hops + 1, 2), dtype=torch.float64, device=dev)
+                for c0 in range(0, n, cb):
+                    c = min(cb, n - c0)
+                    w = work.reshape(-1)[:3 * n * c].view(3, n, c)
+                    o = out.reshape(-1)[:len(sc) * n * c].view(len(sc), n, c)
+                    _wav.cheb_wavelet_block(csr, self.lmax, coeffs, c0, c, thr, w, o)
+                    check(lib.hsd_ring_reduce(engine._ptr(o), len(sc), n, c, engine._ptr(rings.bitmaps),
+                                              engine._ptr(sizes), engine._ptr(rings.orig_of), hops, c0,
+                                              engine._ptr(part), engine._stream()))
+                emb[:, s0:s0 + len(sc)] = part
+        else:
+            L = torch.as_tensor(np.asarray(self.L, dtype=np.float64), device=dev)
+            eig = torch.linalg.eigh(L)
+            for si, s in enumerate(scales):
+                psi = _wav.exact_wavelets_dense(L, s, self.THRESHOLD_COEFF, eig)
+                part = torch.zeros((n, 1, hops + 1, 2), dtype=torch.float64, device=dev)
+                psiT = psi.t().contiguous().view(1, n, n)   # psiT[0, v, c] = Psi[c, v]
+                check(lib.hsd_ring_reduce(engine._ptr(psiT), 1, n, n, engine._ptr(rings.bitmaps),
+                                          engine._ptr(sizes), engine._ptr(rings.orig_of), hops, 0,
+                                          engine._ptr(part), engine._stream()))
+                emb[:, si:si + 1] = part
+        return emb
+
+    def _emb_to_dict(self, emb: torch.Tensor, stat: str) -> dict:
+        e = emb.cpu().numpy()
+        flat = e.reshape(self.n_node, -1) if stat == "triple" else e[..., 0].reshape(self.n_node, -1)
+        out = defaultdict(list)
+        for i, node in enumerate(self.nodes):
+            out[node] = flat[i].tolist()
+        return out
+
+    # embed nodes into vectors using multi-scale wavelets (model/multiscale_HSD.py:35-42)
+    def embed(self, approx=True) -> dict:
+        return self._emb_to_dict(self.embed_device(approx=approx), "triple")
+
+    def _ring_stats_of_row(self, wavelets, node):
+        """[sum, mean] per hop of one caller-supplied wavelet row, through hsd_ring_reduce."""
+        i = self.node2idx[node]
+        rings = self._rings()
+        dev = self._device()
+        row = torch.as_tensor(np.ascontiguousarray(np.asarray(wavelets, dtype=np.float64)[i]), device=dev)
+        part = torch.zeros((self.n_node, 1, self.hop + 1, 2), dtype=torch.float64, device=dev)
+        check(lib.hsd_ring_reduce(engine._ptr(row.view(1, self.n_node, 1)), 1, self.n_node, 1,
+                                  engine._ptr(rings.bitmaps), engine._ptr(rings.sizes.contiguous()),
+                                  engine._ptr(rings.orig_of), self.hop, i, engine._ptr(part), engine._stream()))
+        return part[i, 0].cpu().numpy()
+
+    def get_triple(self, wavelets: np.ndarray, node: str) -> list:
+        """model/multiscale_HSD.py:45-61: [sum, mean] per hop, [0, 0] for an empty ring."""
+        return self._ring_stats_of_row(wavelets, node).reshape(-1).tolist()
+
+    def get_layer_sum(self, wavelets: np.ndarray, node: str) -> list:
+        """model/multiscale_HSD.py:64-73: ring sums only."""
+        return self._ring_stats_of_row(wavelets, node)[:, 0].tolist()
+
+    def parallel_embed(self, n_workers=None) -> dict:
+        """model/multiscale_HSD.py:76-98 (n_workers is accepted and ignored)."""
+        self.embeddings = self.embed()
+        return self.embeddings
+
+    def parallel_calculate_structural_distance(self, n_workers: int = None):
+        """model/multiscale_HSD.py:101-119: sum over scales of
+        HSD.calculate_structural_distance(scale, approx=True)."""
+        total = None
+        for scale in self.scales:
+            D = self.structural_distance_device(float(scale), approx=True)
+            total = D.to(torch.float64) if total is None else total + D
+        return total.cpu().numpy()

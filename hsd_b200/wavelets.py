@@ -1,0 +1,111 @@
+"""Heat-kernel wavelets Psi_s = exp(-s L) on the device.
+
+Reference: HSD.calculate_wavelets (model/HSD.py:48-67) and
+GraphWave.calculate_wavelets (model/GraphWave.py:29-49): either pygsp's
+Chebyshev approximation applied to one unit impulse at a time, or a dense
+``eigh``; then the threshold ``x if x > coeff/N else 0``.
+
+Here the Chebyshev path is one CSR SpMM kernel over a block of impulse columns
+(hsd_cheb_spmm); the exact path uses the vendor eigensolver through torch
+(cuSOLVER, FP64) — a plain library call, it is the step *before* the hot path.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import engine
+from ._lib import check, lib
+from .graph import CSRGraph
+
+
+def cheby_coefficients(scale: float, lmax: float, order: int) -> np.ndarray:
+    """Chebyshev coefficients of g(x) = exp(-scale * x) on [0, lmax] by
+    (order+1)-point Chebyshev-Gauss quadrature — what pygsp's compute_cheby_coeff
+    returns for Heat(tau = scale * lmax) (call site model/HSD.py:52-53)."""
+    n = order + 1
+    theta = np.pi * (np.arange(n) + 0.5) / n
+    g = np.exp(-scale * (lmax / 2.0) * (np.cos(theta) + 1.0))
+    k = np.arange(order + 1)[:, None]
+    return (2.0 / n) * (np.cos(k * theta[None, :]) @ g)
+
+
+def estimate_lmax(g: CSRGraph) -> float:
+    """pygsp Graph.estimate_lmax: 1.01 x the largest Laplacian eigenvalue from
+    ARPACK (k=1, tol=5e-3, ncv=min(N,10)); call sites model/HSD.py:51,
+    model/multiscale_HSD.py:28.  A fixed-seed start vector makes it reproducible."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    n = g.n
+    rows = np.repeat(np.arange(n), np.diff(g.rowptr))
+    keep = rows != g.col
+    A = sp.csr_matrix((np.ones(int(keep.sum())), (rows[keep], g.col[keep])), shape=(n, n))
+    L = sp.diags(np.asarray(A.sum(1)).ravel()) - A
+    if n < 12:
+        lam = float(np.linalg.eigvalsh(L.toarray())[-1])
+    else:
+        lam = float(spla.eigsh(L.tocsc(), k=1, tol=5e-3, ncv=min(n, 10), v0=np.random.default_rng(0).standard_normal(n),
+                               return_eigenvectors=False)[0])
+    return 1.01 * lam
+
+
+class DeviceCSR:
+    """CSR in ORIGINAL node order on the device (the Laplacian of the SpMM)."""
+
+    def __init__(self, g: CSRGraph, device=None):
+        dev = device or engine.require_cuda()
+        self.n = g.n
+        self.rowptr = torch.from_numpy(g.rowptr).to(dev)
+        self.col = torch.from_numpy(g.col).to(dev) if g.col.size else torch.zeros(1, dtype=torch.int32, device=dev)
+
+
+def column_block(n: int, n_scales: int, budget_bytes: float = 8e9) -> int:
+    c = int(budget_bytes / ((3 + n_scales) * n * 8))
+    c = max(32, min(n, c))
+    return c if c == n else max(32, c // 32 * 32)
+
+
+def cheb_wavelet_block(csr: DeviceCSR, lmax: float, coeffs: np.ndarray, col0: int, n_cols: int,
+                       threshold: float, work: Optional[torch.Tensor] = None,
+                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[s, v, c] = Psi_{s}[col0 + c, v] for a block of impulse columns (float64).
+    coeffs: host float64[n_scales, order+1]."""
+    coeffs = np.ascontiguousarray(coeffs, dtype=np.float64)
+    n_scales, order1 = coeffs.shape
+    dev = csr.rowptr.device
+    if work is None:
+        work = torch.empty((3, csr.n, n_cols), dtype=torch.float64, device=dev)
+    if out is None:
+        out = torch.empty((n_scales, csr.n, n_cols), dtype=torch.float64, device=dev)
+    check(lib.hsd_cheb_spmm(engine._ptr(csr.rowptr), engine._ptr(csr.col), csr.n, float(lmax),
+                            coeffs.ctypes.data, n_scales, order1 - 1, col0, n_cols, float(threshold),
+                            engine._ptr(work), engine._ptr(out), engine._stream()))
+    return out
+
+
+def cheb_wavelets_dense(csr: DeviceCSR, scale: float, lmax: float, order: int,
+                        thr_coeff: Optional[float]) -> torch.Tensor:
+    """Full N x N Psi (row i = response to impulse i, model/HSD.py:59) — reference-sized graphs."""
+    n = csr.n
+    thr = -np.inf if thr_coeff is None else thr_coeff * 1.0 / n
+    coeffs = cheby_coefficients(scale, lmax, order)[None, :]
+    psi = torch.empty((n, n), dtype=torch.float64, device=csr.rowptr.device)
+    cb = column_block(n, 1)
+    for c0 in range(0, n, cb):
+        c = min(cb, n - c0)
+        blk = cheb_wavelet_block(csr, lmax, coeffs, c0, c, thr)
+        psi[c0:c0 + c, :] = blk[0].t()
+    return psi
+
+
+def exact_wavelets_dense(L: torch.Tensor, scale: float, thr_coeff: Optional[float],
+                         eig=None) -> torch.Tensor:
+    """U diag(exp(-s lambda)) U^T then threshold (model/HSD.py:61-66), FP64 on device."""
+    lam, U = eig if eig is not None else torch.linalg.eigh(L)
+    psi = (U * torch.exp(-scale * lam)[None, :]) @ U.t()
+    if thr_coeff is not None:
+        thr = thr_coeff * 1.0 / L.shape[0]
+        psi = torch.where(psi > thr, psi, torch.zeros((), dtype=psi.dtype, device=psi.device))
+    return psi

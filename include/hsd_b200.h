@@ -138,6 +138,20 @@ int hsd_pairwise_aligned(const double* vals, const int64_t* offsets, const int32
                          int32_t metric, int32_t row0, int32_t n_rows,
                          double* out, int64_t ld_out, void* stream);
 
+/* ---- K3 (row worker exactly as written, model/HSD.py:140-161) ---------------
+ * out[i*ld + j] = sum_{h < hop_end} aligned(Psi[i, ring_h(i)], Psi[i, ring_h(j)]) for
+ * j > i, 0 for j <= i; BOTH signals come from wavelet row i (the reference indexes q
+ * with startIndex, :155) and hops run 0..hop-1 (:148).  Inputs per row i:
+ *   sorted_vals[i][t]  t-th smallest value of Psi[i, :]   (double[n][n])
+ *   order[i][t]        the node holding it                 (int32[n][n])
+ * ring bitmaps/sizes rows are original indices; bit_of maps original index -> bit id
+ * (NULL: identity). metric as in hsd_pairwise_aligned. */
+int hsd_pairwise_worker(const double* sorted_vals, const int32_t* order,
+                        const uint32_t* ring_bitmaps, const int32_t* ring_sizes,
+                        const int32_t* bit_of, int32_t n_nodes, int32_t hops, int32_t hop_end,
+                        int32_t metric, int32_t row0, int32_t n_rows,
+                        double* out, int64_t ld_out, void* stream);
+
 /* ---- K4: Chebyshev heat-kernel wavelets as CSR SpMM -------------------------
  * Replaces pygsp cheby_op as driven one impulse at a time by model/HSD.py:50-59
  * (and model/GraphWave.py:31-39).  Computes, for a block of n_cols impulse

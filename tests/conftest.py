@@ -29,6 +29,16 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
+def nx_graph(golden_graphs, name):
+    """networkx graph with the reference's node order and string labels."""
+    import networkx as nx
+    nodes = [str(v) for v in golden_graphs[f"{name}_nodes"]]
+    g = nx.Graph()
+    g.add_nodes_from(nodes)
+    g.add_edges_from((nodes[u], nodes[v]) for u, v in golden_graphs[f"{name}_edges"])
+    return g
+
+
 @pytest.fixture(scope="session")
 def golden_graphs():
     return np.load(os.path.join(GOLDEN, "graphs.npz"), allow_pickle=False)
@@ -47,5 +57,8 @@ def robust_csv():
 @pytest.fixture(scope="session", autouse=True)
 def _built_library():
     # the .so travels with the repo snapshot; build it when missing (nvcc cross-compiles without a GPU)
-    from hsd_b200.build import build_library
-    build_library()
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_hsd_build", os.path.join(ROOT, "hsd_b200", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.build_library()

@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""bench.py — HSD node-pairs/sec for the degree-mode 3-hop distance matrix.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--workload c2|c3|NODESxHOPS]
+
+One "step" = one full pass of the hot path over the workload graph: k-hop rings
+(BFS kernel) -> per-ring degree CDF signatures -> (N>1: one NCCL all-gather of
+the signature table) -> pairwise W1 (L1 between signatures) for this rank's rows.
+`value` is whole-job unordered node pairs / second with the graph already in HBM;
+`e2e` is the same job through the host-buffer pipeline (pinned host CSR in, pinned
+host float32 matrix out, copies inside the timed region).
+
+Workload (BASELINE.json configs[1]): networkx.barabasi_albert_graph(20000, 5, seed=0),
+3 hops, full N x N.  With N>1 ranks the SAME graph is row-block sharded (strong scaling).
+
+`--impl reference` times the reference's CPU algorithm for this path (the oracle
+port: Python BFS rings of tools/hierarchy.py + scipy.stats.wasserstein_distance per
+pair and hop, model/HSD.py:98-114) on the box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "HSD node-pairs/sec (3-hop distance matrix)"
+UNIT = "node-pairs/s"
+
+
+def parse_workload(spec: str):
+    if spec == "c2":
+        return 20000, 3
+    if spec == "c3":
+        return 100000, 4
+    n, h = spec.lower().split("x")
+    return int(n), int(h)
+
+
+# ------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle port on host cores, bounded sample
+# ------------------------------------------------------------------------------
+_POOL_STATE = {}
+
+
+def _pool_init(n, edges, hops):
+    from oracle import hsd_oracle as O
+    _POOL_STATE["adj"] = O.adjacency_from_edges(n, edges)
+    _POOL_STATE["hops"] = hops
+    _POOL_STATE["deg"] = np.array([len(a) for a in _POOL_STATE["adj"]], dtype=np.float64)
+
+
+def _pool_rings(src):
+    from oracle import hsd_oracle as O
+    t = time.perf_counter()
+    layers = O.rings_of(_POOL_STATE["adj"], int(src), _POOL_STATE["hops"])
+    deg = _POOL_STATE["deg"]
+    sig = [deg[np.asarray(l, dtype=np.int64)] for l in layers]
+    return int(src), sig, time.perf_counter() - t
+
+
+def _pool_pairs(args):
+    from oracle import hsd_oracle as O
+    sig_i, sig_js = args
+    t = time.perf_counter()
+    out = [sum(O.w1(sig_i[h], sj[h]) for h in range(len(sig_i))) for sj in sig_js]
+    return out, time.perf_counter() - t
+
+
+class CpuReference:
+    """model/HSD.py:98-114 with a degree-valued ring signal, through the oracle, on all host cores."""
+
+    def __init__(self, n, hops, sample_nodes=48, seed=0):
+        import multiprocessing as mp
+        import networkx as nx
+        self.n, self.hops = n, hops
+        g = nx.barabasi_albert_graph(n, 5, seed=seed)
+        self.edges = np.array(g.edges(), dtype=np.int64)
+        self.cores = os.cpu_count() or 1
+        self.sample = np.sort(np.random.default_rng(seed).choice(n, size=min(sample_nodes, n), replace=False))
+        self.pool = mp.get_context("fork").Pool(self.cores, initializer=_pool_init,
+                                                initargs=(n, self.edges, hops))
+
+    def step(self):
+        """One bounded pass: rings of the sampled sources + all pairs among them.
+        Returns (extrapolated full-workload pairs/s, details)."""
+        t0 = time.perf_counter()
+        res = self.pool.map(_pool_rings, list(self.sample), chunksize=max(1, len(self.sample) // (4 * self.cores)))
+        t_rings_wall = time.perf_counter() - t0
+        sigs = [r[1] for r in res]
+        ring_cpu = sum(r[2] for r in res)
+        s = len(sigs)
+        t1 = time.perf_counter()
+        jobs = [(sigs[i], sigs[i + 1:]) for i in range(s - 1)]
+        out = self.pool.map(_pool_pairs, jobs, chunksize=1)
+        t_pairs_wall = time.perf_counter() - t1
+        pair_cpu = sum(o[1] for o in out)
+        n_pairs = s * (s - 1) // 2
+        # full job on `cores` cores: N ring builds + N(N-1)/2 pair evaluations
+        full_pairs = self.n * (self.n - 1) / 2
+        t_full = (self.n * (ring_cpu / s) + full_pairs * (pair_cpu / n_pairs)) / self.cores
+        return full_pairs / t_full, dict(sample_nodes=s, sample_pairs=n_pairs, rings_wall_s=t_rings_wall,
+                                         pairs_wall_s=t_pairs_wall, ring_cpu_s_per_source=ring_cpu / s,
+                                         pair_cpu_s=pair_cpu / n_pairs, step_wall_s=time.perf_counter() - t0)
+
+    def describe(self, d):
+        return (f"{d['sample_nodes']} sampled sources: Python BFS rings ({d['ring_cpu_s_per_source']*1e3:.1f} ms/source) + "
+                f"{d['sample_pairs']} pairs x {self.hops + 1} hops of scipy wasserstein_distance "
+                f"({d['pair_cpu_s']*1e6:.0f} us/pair), extrapolated to N={self.n} on {self.cores} cores "
+                f"(perfect scaling assumed)")
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n, hops = parse_workload(args.workload)
+    ref = CpuReference(n, hops)
+    for _ in range(args.warmup):
+        ref.step()
+    vals, last = [], None
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        v, last = ref.step()
+        vals.append(v)
+    wall = time.perf_counter() - t0
+    ref.close()
+    value = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / max(args.steps, 1) * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"barabasi_albert_graph({n}, 5, seed=0), {hops} hops, degree-valued ring signal, full NxN",
+                   "n_nodes": n, "hops": hops},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": ref.cores, "kind": "port",
+                         "sample": ref.describe(last)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------
+# clocks sampling (NVML) during the timed region
+# ------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------
+# native arm
+# ------------------------------------------------------------------------------
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    from hsd_b200 import engine
+    from hsd_b200.graph import powerlaw_graph
+    from hsd_b200.sharded import ShardedDegreeHSD, shard_rows
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (native arm) needs a CUDA device: hsd_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n, hops = parse_workload(args.workload)
+    g = powerlaw_graph(n, 5, seed=0)       # same deterministic graph on every rank
+    dg = engine.DeviceGraph.upload(g, device=dev)
+    plan = ShardedDegreeHSD(dg, hops, rank, world)
+    pairs = n * (n - 1) / 2
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
+
+    # live FP32 CUDA-core issue peak (the pairwise kernel's roofline denominator)
+    fp32_peak = engine.fp32_issue_peak()
+
+    def one_step(ev=None):
+        flush.fill_(1.0)                   # evict the previous step's tables from L2
+        if ev is not None:
+            ev[0].record()
+        plan.signatures()
+        if ev is not None:
+            ev[1].record()
+        plan.gather()
+        n_ = dg.n
+        engine.signature_transpose(plan.sig_all[:n_], plan.k_used, plan.sigT, 0)
+        if ev is not None:
+            ev[2].record()
+        if plan.n_rows:
+            if world == 1:
+                engine.pairwise_l1(plan.sigT, n_, symmetric=True, out=plan.out)
+            else:
+                engine.pairwise_l1(plan.sigT, n_, plan.row0, plan.n_rows, 0, n_, symmetric=False, out=plan.out)
+        if ev is not None:
+            ev[3].record()
+
+    for _ in range(max(args.warmup, 0)):
+        one_step()
+    torch.cuda.synchronize()
+    plan.check()
+
+    events = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    sampler = ClockSampler(local_rank)
+    barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.steps):
+        one_step(events[k])
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    clocks = sampler.stop()
+    total_ms = max_over_ranks(e0.elapsed_time(e1))
+    ms_per_step = total_ms / args.steps
+    value = pairs / (ms_per_step * 1e-3)
+
+    bfs_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in events]))
+    gather_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in events]))
+    pair_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in events]))
+
+    # ---- roofline of the dominant kernel (pairwise L1) ----
+    # algorithmic flops per launch = 2 (subtract, |.|-accumulate) x unordered pairs this launch
+    # covers x signature length; hop 0 is one scalar (the kernel treats it so), every later hop B-1 gaps
+    k_alg = plan.k_used
+    if world == 1:
+        launch_pairs = pairs
+    else:
+        launch_pairs = plan.n_rows * n      # ordered (row, col) pairs of this rank's block
+    flops = 2.0 * launch_pairs * k_alg
+    achieved = flops / (pair_ms * 1e-3) / 1e12 if pair_ms > 0 else 0.0
+    roofline = {
+        "kernel": "pairwise_l1_kernel", "bound": "fp32", "achieved": achieved, "peak": fp32_peak / 1e12,
+        "unit": "TFLOP/s", "frac": achieved / (fp32_peak / 1e12), "traffic": None,
+        "peak_source": "measured live: hsd_fp32_peak_probe (register-only FADD sub+|.|-accumulate), "
+                       "1 flop per lane per clock; MEASURED_PEAKS.json has no FP32 CUDA-core entry",
+        "flops_per_launch": flops, "ms_per_launch": pair_ms,
+        "note": "tensor cores not applicable (|a-b| is not a contraction); FMA-counted peak would be 2x this",
+    }
+    # ---- secondary: BFS + signature kernel against HBM/L2 ----
+    sig_rows = plan.sig_all[plan.row0:plan.row0 + plan.n_rows, 1:k_alg].double()
+    nb1 = dg.n_bins - 1
+    sizes = plan.sizes[plan.row0:plan.row0 + plan.n_rows].double()
+    sup_max, sup_min = float(dg.support[-1]), float(dg.support[0])
+    edges_scanned = float((plan.sig_all[plan.row0:plan.row0 + plan.n_rows, 0].double()).sum().item())  # hop 0 expands the source
+    for h in range(1, hops):   # rings 1..H-1 are expanded; sum of member degrees = n * mean = n * (max - sum_b CDF*delta)
+        mean_deg = sup_max - sig_rows[:, (h - 1) * nb1:h * nb1].sum(1)
+        edges_scanned += float((sizes[:, h] * mean_deg).sum().item())
+    bfs_bytes = 4.0 * edges_scanned + 4.0 * k_alg * plan.n_rows
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    roofline_bfs = {
+        "kernel": "bfs_ring_signature_kernel", "bound": "hbm", "achieved": bfs_bytes / (bfs_ms * 1e-3) / 1e9,
+        "peak": hbm_peak, "unit": "GB/s", "frac": bfs_bytes / (bfs_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+        "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+        "bytes_per_launch": bfs_bytes, "ms_per_launch": bfs_ms, "edges_scanned_per_launch": edges_scanned,
+        "note": "CSR (1 MB) and bitmaps are L2/SMEM resident, so HBM fraction is structurally small (SURVEY H4)",
+    }
+
+    # ---- e2e: host buffers in, host matrix out, copies inside the timed region ----
+    pipe = engine.HostDegreePipeline(g, hops, device=dev, row0=plan.row0 if world > 1 else 0,
+                                     n_rows=plan.n_rows if world > 1 else n)
+    host_out = torch.empty((pipe.n_rows, n), dtype=torch.float32).pin_memory()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        pipe.run(host_out)
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        pipe.run(host_out)          # run() synchronises the copy stream: the result is in host memory
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
+    barrier()
+    e2e = {"value": pairs / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": int(pipe.h2d_bytes), "d2h_bytes_per_step": int(pipe.d2h_bytes),
+           "api": "hsd_b200.engine.HostDegreePipeline.run (what HSD.calculate_structural_distance(out=pinned) calls)",
+           "checksum": float(host_out[: min(64, pipe.n_rows)].double().sum().item())}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ref = CpuReference(n, hops)
+        v, d = ref.step()
+        ref.close()
+        cpu = {"value": v, "unit": UNIT, "cores": ref.cores, "kind": "port", "sample": ref.describe(d)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"barabasi_albert_graph({n}, 5, seed=0), {hops} hops, degree-valued ring signal, full NxN"
+                                   + (f", row-block sharded over {world} GPUs" if world > 1 else ""),
+                       "n_nodes": n, "hops": hops, "support_bins": dg.n_bins, "signature_len": k_alg,
+                       "l2": "256 MB buffer written before every step (flush) + each step writes a result > L2",
+                       "symmetric": world == 1},
+            "stage_ms": {"bfs_signature": bfs_ms, "allgather_transpose": gather_ms, "pairwise": pair_ms},
+            "roofline": roofline, "roofline_bfs": roofline_bfs, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(args.steps * (3 if plan.n_rows else 2)),
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -64,16 +64,16 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         : "memory");
 }
 
-// linear index over the upper triangle (row-major, J >= I) of an nt x nt tile grid
-__device__ __forceinline__ void tri_decode(int t, int nt, int& I, int& J) {
-    const float b = 2.f * nt + 1.f;
-    int i = (int)((b - sqrtf(b * b - 8.f * (float)t)) * 0.5f);
-    i = max(0, min(i, nt - 1));
-    // first(i) = i*nt - i*(i-1)/2
-    while (i > 0 && i * nt - (i * (i - 1)) / 2 > t) --i;
-    while (i + 1 < nt && (i + 1) * nt - ((i + 1) * i) / 2 <= t) ++i;
+// linear index over the tiles (I, J >= I) of a tiles_r x tiles_c trapezoid (row-major);
+// tile row i starts at first(i) = i*tiles_c - i*(i-1)/2
+__device__ __forceinline__ void tri_decode(int t, int tiles_r, int tiles_c, int& I, int& J) {
+    const float b = 2.f * tiles_c + 1.f;
+    int i = (int)((b - sqrtf(fmaxf(b * b - 8.f * (float)t, 0.f))) * 0.5f);
+    i = max(0, min(i, tiles_r - 1));
+    while (i > 0 && i * tiles_c - (i * (i - 1)) / 2 > t) --i;
+    while (i + 1 < tiles_r && (i + 1) * tiles_c - ((i + 1) * i) / 2 <= t) ++i;
     I = i;
-    J = i + (t - (i * nt - (i * (i - 1)) / 2));
+    J = i + (t - (i * tiles_c - (i * (i - 1)) / 2));
 }
 
 struct PairArgs {
@@ -93,7 +93,7 @@ pairwise_l1_kernel(const __grid_constant__ CUtensorMap tmap, const PairArgs p) {
 
     int I, J;
     if (p.symmetric) {
-        tri_decode(blockIdx.x, p.tiles_r, I, J);
+        tri_decode(blockIdx.x, p.tiles_r, p.tiles_c, I, J);
     } else {
         I = blockIdx.x / p.tiles_c;
         J = blockIdx.x - I * p.tiles_c;
@@ -249,7 +249,7 @@ extern "C" int hsd_pairwise_l1(const float* sigT, int32_t k_pad, int64_t n_pad, 
     HSD_REQUIRE((reinterpret_cast<uintptr_t>(sigT) & 15) == 0, "sigT must be 16-byte aligned");
     HSD_REQUIRE(row0 >= 0 && col0 >= 0 && n_rows >= 0 && n_cols >= 0, "negative range");
     HSD_REQUIRE(row0 + (int64_t)n_rows <= n_pad && col0 + (int64_t)n_cols <= n_pad, "range exceeds n_pad");
-    HSD_REQUIRE(!symmetric || (row0 == col0 && n_rows == n_cols), "symmetric needs equal ranges");
+    HSD_REQUIRE(!symmetric || (row0 == col0 && n_cols >= n_rows), "symmetric needs row0 == col0 and n_cols >= n_rows");
     if (n_rows == 0 || n_cols == 0) return HSD_OK;
 
     auto encode = get_encode();
@@ -278,7 +278,7 @@ extern "C" int hsd_pairwise_l1(const float* sigT, int32_t k_pad, int64_t n_pad, 
     a.symmetric = symmetric ? 1 : 0;
     a.out = out; a.ld = ld_out;
     a.vec_ok = (ld_out % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-    const long long n_tiles = symmetric ? (long long)a.tiles_r * (a.tiles_r + 1) / 2
+    const long long n_tiles = symmetric ? (long long)a.tiles_r * a.tiles_c - (long long)a.tiles_r * (a.tiles_r - 1) / 2
                                         : (long long)a.tiles_r * a.tiles_c;
     HSD_REQUIRE(n_tiles < (1ll << 31), "too many tiles for one launch");
 

@@ -210,3 +210,105 @@ def fp32_issue_peak(iters: int = 20000, reps: int = 3) -> float:
         e1.synchronize()
         best = max(best, ops.value / (e0.elapsed_time(e1) * 1e-3))
     return best
+
+
+# --------------------------------------------------------------------------
+# host-buffer pipeline (the e2e path: host CSR in, host matrix out)
+# --------------------------------------------------------------------------
+def _pin(a: np.ndarray) -> torch.Tensor:
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    return t.pin_memory() if torch.cuda.is_available() else t
+
+
+class HostDegreePipeline:
+    """Degree-mode HSD from HOST buffers to a HOST result, copies included.
+
+    Inputs (pinned): the degree-ordered CSR and support tables of a CSRGraph.
+    Output: float32 rows [row0, row0+n_rows) x N written into a pinned host tensor.
+    The pairwise kernel runs panel by panel (symmetric trapezoids on one GPU, plain row
+    blocks when the rows are a shard); each finished panel is copied device->host on a
+    second stream while the next one computes, so the PCIe transfer of the result — the
+    dominant cost at N = 20k (1.6 GB) — overlaps the kernels."""
+
+    def __init__(self, g: CSRGraph, hops: int, empty: str = "raise", device=None,
+                 row0: int = 0, n_rows: Optional[int] = None, n_chunks: int = 8):
+        self.dev = device or require_cuda()
+        self.g, self.hops, self.empty = g, hops, empty
+        o = g.degree_order()
+        sup, bin_end, delta = o.support(include_zero=(empty == "zero"))
+        if delta.size == 0:
+            delta = np.zeros(1, dtype=np.float32)
+        self.n = g.n
+        self.n_bins = int(sup.size)
+        self.heavy_begin = o.heavy_begin
+        self.host = {k: _pin(v) for k, v in dict(rowptr=o.rowptr, col=o.col if o.col.size else np.zeros(1, np.int32),
+                                                 orig_of=o.orig_of, new_of=o.new_of, bin_end=bin_end,
+                                                 delta=delta).items()}
+        self.dev_in = {k: torch.empty_like(v, device=self.dev) for k, v in self.host.items()}
+        self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.host.values())
+        self.k_used = 1 + hops * (self.n_bins - 1)
+        self.row0 = row0
+        self.n_rows = self.n - row0 if n_rows is None else n_rows
+        self.full = (row0 == 0 and self.n_rows == self.n)
+        self.sig = torch.zeros((self.n, roundup(self.k_used, 4)), dtype=torch.float32, device=self.dev)
+        self.sigT = alloc_signature_table(self.k_used, self.n, self.dev)
+        self.out_rows_idx = torch.arange(self.n, dtype=torch.int32, device=self.dev)
+        self.status = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.D = torch.empty((self.n_rows, self.n), dtype=torch.float32, device=self.dev)
+        self.d2h_bytes = self.n_rows * self.n * 4
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
+        self.panels = self._plan_panels(n_chunks)
+        self.launches_per_step = 2 + len(self.panels)
+
+    def _plan_panels(self, n_chunks: int):
+        """Row panels (multiples of the 128-row tile).  Symmetric mode: tile row I costs
+        (nt - I) tiles, so equal-work panels start narrow — the first copy starts early."""
+        nt = (self.n_rows + PAIR_TILE - 1) // PAIR_TILE
+        n_chunks = max(1, min(n_chunks, nt))
+        if self.full:
+            ntc = (self.n + PAIR_TILE - 1) // PAIR_TILE
+            work = np.cumsum([ntc - i for i in range(nt)])
+        else:
+            work = np.cumsum(np.ones(nt))
+        cuts = [0]
+        for c in range(1, n_chunks):
+            t = int(np.searchsorted(work, work[-1] * c / n_chunks)) + 1
+            if t > cuts[-1] and t < nt:
+                cuts.append(t)
+        cuts.append(nt)
+        return [(a * PAIR_TILE, min(b * PAIR_TILE, self.n_rows) - a * PAIR_TILE) for a, b in zip(cuts[:-1], cuts[1:])]
+
+    def run(self, out: torch.Tensor) -> torch.Tensor:
+        """out: pinned float32 host tensor [n_rows, N]. Returns it (synchronised)."""
+        if out.shape != (self.n_rows, self.n) or out.dtype != torch.float32:
+            raise ValueError("out must be float32 of shape (n_rows, N)")
+        cur = torch.cuda.current_stream(self.dev)
+        for k, v in self.host.items():
+            self.dev_in[k].copy_(v, non_blocking=True)
+        d = self.dev_in
+        self.status.zero_()
+        check(lib.hsd_ring_signature_degree(
+            _ptr(d["rowptr"]), _ptr(d["col"]), self.n, _ptr(d["new_of"]), _ptr(self.out_rows_idx), self.n,
+            self.hops, self.heavy_begin, _ptr(d["bin_end"]), _ptr(d["delta"]), self.n_bins,
+            _ptr(self.sig), self.sig.stride(0), None, None, 1 if self.empty == "zero" else 0,
+            _ptr(self.status), _stream()))
+        signature_transpose(self.sig, self.k_used, self.sigT, 0)
+        for (p0, pr) in self.panels:
+            if self.full:
+                # trapezoid: rows [p0, p0+pr) x cols [p0, N), mirrored into rows below
+                view = self.D[p0:, p0:]
+                check(lib.hsd_pairwise_l1(_ptr(self.sigT), self.sigT.shape[0], self.sigT.stride(0),
+                                          p0, pr, p0, self.n - p0, 1, view.data_ptr(), self.D.stride(0), _stream()))
+            else:
+                view = self.D[p0:]
+                check(lib.hsd_pairwise_l1(_ptr(self.sigT), self.sigT.shape[0], self.sigT.stride(0),
+                                          self.row0 + p0, pr, 0, self.n, 0, view.data_ptr(), self.D.stride(0), _stream()))
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self.copy_stream.wait_event(ev)
+            with torch.cuda.stream(self.copy_stream):
+                out[p0:p0 + pr].copy_(self.D[p0:p0 + pr], non_blocking=True)
+        self.copy_stream.synchronize()
+        if self.empty == "raise" and int(self.status.item()) & 1:
+            raise EmptyRingError("Distribution can't be empty.")
+        return out

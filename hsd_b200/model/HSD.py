@@ -72,6 +72,7 @@ class HSD(object):
         self._dcsr = None
         self._ringset = None
         self._ringset_src = None
+        self._host_pipe = None
 
     # ---- lazy dense matrices (model/HSD.py:33-34) ----
     @property
@@ -200,6 +201,14 @@ class HSD(object):
         """model/HSD.py:98-114: D[i, j] = sum_{h=0..hop} W1(ring signal_i[h], ring signal_j[h]).
         Returns a float64 ndarray like the reference; ``out`` (a pinned float32/float64
         host tensor or ndarray of shape (N, N)) receives the result instead when given."""
+        if out is not None and self.signal == "degree":
+            # host-buffer pipeline: H2D of the CSR, kernels, and the D2H of finished row panels
+            # overlapped with the panels still computing (engine.HostDegreePipeline)
+            dst = out if isinstance(out, torch.Tensor) else torch.from_numpy(out)
+            if self._host_pipe is None or self._host_pipe.g is not self.csr or self._host_pipe.hops != self.hop:
+                self._host_pipe = engine.HostDegreePipeline(self.csr, self.hop, empty=self.empty, device=self._device())
+            self._host_pipe.run(dst)
+            return out
         D = self.structural_distance_device(scale, approx)
         if out is not None:
             dst = out if isinstance(out, torch.Tensor) else torch.from_numpy(out)

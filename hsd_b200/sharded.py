@@ -1,0 +1,92 @@
+"""Row-block sharding of the degree-mode path over the GPUs of one box.
+
+One process per GPU (torch.distributed, NCCL).  Every D[i, j] depends only on
+signature rows i and j, so rank r owns a contiguous block of rows: it runs the
+BFS + degree-CDF kernel for its own sources, contributes its slice of the
+signature table with ONE in-place all-gather (the only collective on the path;
+SURVEY.md §8 e), and computes its rows of D against all columns.  The result
+stays sharded on the devices.
+
+The reference's counterpart is multiprocessing.Pool over rows with the whole
+model pickled per task (model/HSD.py:118-137).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import engine
+
+
+def shard_rows(n: int, world: int, rank: int) -> Tuple[int, int, int]:
+    """(row0, n_rows, rows_per_rank): contiguous blocks of ceil(n / world) rows, the last
+    ranks may own fewer (or zero) rows; rows_per_rank is the all-gather chunk."""
+    per = (n + world - 1) // world
+    row0 = min(rank * per, n)
+    return row0, max(0, min(per, n - row0)), per
+
+
+class ShardedDegreeHSD:
+    """Plan + buffers for repeated evaluation of one graph on `world` ranks."""
+
+    def __init__(self, dg: engine.DeviceGraph, hops: int, rank: int = 0, world: int = 1,
+                 group=None, empty: str = "raise"):
+        self.dg, self.hops, self.rank, self.world, self.group, self.empty = dg, hops, rank, world, group, empty
+        n = dg.n
+        dev = dg.rowptr.device
+        self.row0, self.n_rows, self.per = shard_rows(n, world, rank)
+        self.k_used = dg.k_used(hops)
+        self.ld = engine.roundup(self.k_used, 4)
+        # row-major signature table, padded to world * per rows so every rank's chunk is equal
+        self.sig_all = torch.zeros((world * self.per, self.ld), dtype=torch.float32, device=dev)
+        self.sigT = engine.alloc_signature_table(self.k_used, n, dev)
+        self.rows = torch.arange(self.row0, self.row0 + self.n_rows, dtype=torch.int32, device=dev)
+        self.src = dg.new_of[self.rows.long()].contiguous()
+        self.out_rows = torch.arange(self.row0, self.row0 + self.n_rows, dtype=torch.int32, device=dev)
+        self.sizes = torch.zeros((world * self.per, hops + 1), dtype=torch.int32, device=dev)
+        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.out = torch.empty((max(self.n_rows, 1), n), dtype=torch.float32, device=dev)
+        self.launches_per_step = 3
+
+    def signatures(self) -> None:
+        """BFS + degree CDF for this rank's sources, written straight into its slice of the
+        gathered table."""
+        from ._lib import check, lib
+        dg = self.dg
+        if self.n_rows == 0:
+            return
+        check(lib.hsd_ring_signature_degree(
+            engine._ptr(dg.rowptr), engine._ptr(dg.col), dg.n, engine._ptr(self.src),
+            engine._ptr(self.out_rows), self.n_rows, self.hops, dg.heavy_begin,
+            engine._ptr(dg.bin_end), engine._ptr(dg.delta), dg.n_bins,
+            engine._ptr(self.sig_all), self.ld, engine._ptr(self.sizes), None,
+            1 if self.empty == "zero" else 0, engine._ptr(self.status), engine._stream()))
+
+    def gather(self) -> None:
+        """The one collective: in-place all-gather of the signature table (NCCL over NVLink)."""
+        if self.world == 1:
+            return
+        import torch.distributed as dist
+        chunk = self.sig_all[self.rank * self.per:(self.rank + 1) * self.per]
+        dist.all_gather_into_tensor(self.sig_all, chunk, group=self.group)
+
+    def distances(self) -> torch.Tensor:
+        n = self.dg.n
+        engine.signature_transpose(self.sig_all, self.k_used, self.sigT, 0) if n == self.sig_all.shape[0] else \
+            engine.signature_transpose(self.sig_all[:n], self.k_used, self.sigT, 0)
+        if self.n_rows == 0:
+            return self.out[:0]
+        if self.world == 1:
+            return engine.pairwise_l1(self.sigT, n, symmetric=True, out=self.out)
+        return engine.pairwise_l1(self.sigT, n, self.row0, self.n_rows, 0, n, symmetric=False, out=self.out)
+
+    def step(self) -> torch.Tensor:
+        self.signatures()
+        self.gather()
+        return self.distances()
+
+    def check(self) -> None:
+        if self.empty == "raise" and int(self.status.item()) & 1:
+            raise engine.EmptyRingError("Distribution can't be empty.")

@@ -93,9 +93,13 @@ int hsd_signature_transpose(const float* sig, int64_t sig_ld, int32_t n_rows, in
  * Replaces the O(N^2 (H+1)) scipy loop model/HSD.py:103-112 (and :144-159).
  *   out[(i-row0)*ld_out + (j-col0)] = sum_k |sigT[k][i] - sigT[k][j]|
  * for i in [row0,row0+n_rows), j in [col0,col0+n_cols).
- * symmetric != 0 requires the two ranges to be equal; only tiles on or above
- * the diagonal are computed and each is also stored mirrored (the reference
- * fills dist_mat[i,j] = dist_mat[j,i] the same way, model/HSD.py:112).
+ * symmetric != 0 requires row0 == col0 and n_cols >= n_rows (a square, or the
+ * trapezoid "rows of a panel x every column from the panel's first row on"); only
+ * tiles on or above the diagonal are computed and each is also stored mirrored at
+ * out[(j-row0)*ld_out + (i-col0)] (so `out` must have n_cols rows), the way the
+ * reference fills dist_mat[i,j] = dist_mat[j,i] (model/HSD.py:112).  Panels of
+ * rows processed in order therefore complete the matrix top to bottom, which is
+ * what lets the host pipeline stream finished rows out while later panels compute.
  * sigT: float[k_pad][n_pad], k_pad % HSD_PAIR_KCHUNK == 0, n_pad % 4 == 0,
  * base 16-byte aligned. Tiles are staged by TMA (cp.async.bulk.tensor.2d). */
 int hsd_pairwise_l1(const float* sigT, int32_t k_pad, int64_t n_pad,

@@ -14,6 +14,7 @@
 // shared memory already in the layout the register tiles read with
 // conflict-free LDS.128.
 #include <cuda.h>
+#include <stdlib.h>
 #include <cudaTypedefs.h>
 #include "hsd_common.cuh"
 
@@ -55,6 +56,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "memory");
     } while (!ok);
 }
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y,
                                             uint32_t bar) {
     asm volatile(
@@ -86,6 +98,7 @@ struct PairArgs {
     int vec_ok;  // float4 stores legal (ld % 4 == 0, base and col0 aligned)
 };
 
+template <int UNROLL>
 __global__ void __launch_bounds__(PAIR_THREADS, 2)
 pairwise_l1_kernel(const __grid_constant__ CUtensorMap tmap, const PairArgs p) {
     extern __shared__ __align__(128) unsigned char pair_smem_raw[];
@@ -135,12 +148,21 @@ pairwise_l1_kernel(const __grid_constant__ CUtensorMap tmap, const PairArgs p) {
 #pragma unroll
         for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
 
+    uint32_t ready = 0;   // phase of the next chunk already observed complete
     for (int c = 0; c < p.k_chunks; ++c) {
         if (tid == 0 && c + LOOKAHEAD < p.k_chunks) issue_chunk(c + LOOKAHEAD);
         const int s = c % STAGES;
         const uint32_t ph = (c / STAGES) & 1;
-        mbar_wait(smem_u32(&sm.full[s]), ph);
-#pragma unroll
+        if (!ready) mbar_wait(smem_u32(&sm.full[s]), ph);
+        // probe the NEXT chunk's barrier now (its TMA was issued a chunk ago): the try_wait's
+        // ~100-cycle latency then hides under this chunk's 2048 FADDs instead of heading the
+        // next chunk's dependency chain
+        ready = (c + 1 < p.k_chunks)
+                    ? mbar_test(smem_u32(&sm.full[(c + 1) % STAGES]), ((c + 1) / STAGES) & 1) : 0u;
+        // Partial unroll on purpose: a fully unrolled 16-step chunk is ~34 KB of SASS, larger
+        // than the 32 KB instruction cache, and the kernel then stalls on instruction fetch
+        // (ncu: stall_no_instruction 0.82 -> 0.09 per issue, profiles/r1_pairwise_notes.md).
+#pragma unroll UNROLL
         for (int kk = 0; kk < KC; ++kk) {
             const float4 a0 = *reinterpret_cast<const float4*>(&sm.a[s][kk][ty * 4]);
             const float4 a1 = *reinterpret_cast<const float4*>(&sm.a[s][kk][64 + ty * 4]);
@@ -283,10 +305,22 @@ extern "C" int hsd_pairwise_l1(const float* sigT, int32_t k_pad, int64_t n_pad, 
     HSD_REQUIRE(n_tiles < (1ll << 31), "too many tiles for one launch");
 
     const int smem = (int)sizeof(PairSmem);
-    HSD_CUDA_TRY(cudaFuncSetAttribute(pairwise_l1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    pairwise_l1_kernel<<<(unsigned)n_tiles, PAIR_THREADS, smem, (cudaStream_t)stream>>>(tmap, a);
-    HSD_CUDA_TRY(cudaGetLastError());
-    return HSD_OK;
+    static int unroll = 0;   // tuning knob, read once: HSD_PAIR_UNROLL in {4, 8, 16}
+    if (!unroll) {
+        const char* e = getenv("HSD_PAIR_UNROLL");
+        unroll = e ? atoi(e) : 8;
+    }
+    auto launch = [&](auto kern) -> int {
+        HSD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        kern<<<(unsigned)n_tiles, PAIR_THREADS, smem, (cudaStream_t)stream>>>(tmap, a);
+        HSD_CUDA_TRY(cudaGetLastError());
+        return HSD_OK;
+    };
+    switch (unroll) {
+        case 4: return launch(pairwise_l1_kernel<4>);
+        case 16: return launch(pairwise_l1_kernel<16>);
+        default: return launch(pairwise_l1_kernel<8>);
+    }
 }
 
 extern "C" int hsd_fp32_peak_probe(float* sink, int32_t iters, int64_t* lane_ops_host, void* stream) {

@@ -1,0 +1,142 @@
+"""Host-side logic that needs no GPU: CSR ingest, degree ordering, support tables,
+sharding / panel plans, the C-ABI surface and its argument validation."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "hsd_b200.h")).read()
+    declared = set(re.findall(r"\b(hsd_[a-z0-9_]+)\s*\(", hdr))
+    from hsd_b200._lib import HEADER_SYMBOLS, lib
+    assert declared == set(HEADER_SYMBOLS), declared ^ set(HEADER_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.hsd_version() >= 100
+
+
+def test_c_abi_argument_validation_without_gpu():
+    """Bad arguments are rejected before any CUDA call, with an error string."""
+    from hsd_b200._lib import HSDError, check, lib
+    rc = lib.hsd_pairwise_l1(None, 16, 128, 0, 1, 0, 1, 0, None, 128, None)
+    assert rc == -1 and b"null" in lib.hsd_last_error_string()
+    buf = (ctypes.c_float * 64)()
+    p = ctypes.addressof(buf)
+    assert lib.hsd_pairwise_l1(p, 15, 128, 0, 1, 0, 1, 0, p, 128, None) == -1     # k_pad % 16
+    assert lib.hsd_pairwise_l1(p, 16, 130, 0, 1, 0, 1, 0, p, 130, None) == -1     # n_pad % 4
+    assert lib.hsd_pairwise_l1(p, 16, 128, 0, 64, 0, 32, 1, p, 128, None) == -1   # symmetric trapezoid
+    assert lib.hsd_ring_signature_degree(None, None, 4, None, None, 1, 2, 0, None, None, 1, None, 0,
+                                         None, None, 0, None, None) == -1
+    assert lib.hsd_pairwise_aligned(p, p, p, 4, 2, 0, 3, 7, 0, 1, p, 4, None) == -1  # metric
+    assert lib.hsd_ring_reduce(p, 1, 4, 4, p, p, None, 9, 0, p, None) == -1          # hops > 7
+    with pytest.raises(HSDError):
+        check(lib.hsd_cheb_spmm(p, p, 4, -1.0, p, 1, 3, 0, 4, 0.0, p, p, None))
+
+
+def test_no_cpu_fallback():
+    import torch
+    from hsd_b200 import engine
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError):
+        engine.require_cuda()
+    with pytest.raises(RuntimeError):
+        engine._ptr(torch.zeros(4))
+    from hsd_b200.graph import powerlaw_graph
+    with pytest.raises(RuntimeError):
+        engine.DeviceGraph.upload(powerlaw_graph(50))
+
+
+def test_csr_from_networkx_keeps_first_appearance_order():
+    import networkx as nx
+    from hsd_b200.graph import CSRGraph
+    g = nx.Graph()
+    g.add_edges_from([("b", "a"), ("a", "c"), ("d", "b"), ("a", "b")])
+    csr = CSRGraph.from_networkx(g)
+    assert csr.nodes == ["b", "a", "c", "d"]                     # tools/util.py:11-24 ordering
+    assert csr.degree.tolist() == [2, 2, 1, 1]
+    assert csr.neighbors(0).tolist() == [1, 3] and csr.neighbors(1).tolist() == [0, 2]
+    A = nx.adjacency_matrix(g).todense()
+    dense = np.zeros((4, 4), dtype=int)
+    for i in range(4):
+        dense[i, csr.neighbors(i)] = 1
+    assert np.array_equal(dense, np.asarray(A).astype(int))
+
+
+def test_degree_order_and_support_tables():
+    from hsd_b200.graph import HEAVY_DEGREE, powerlaw_graph
+    g = powerlaw_graph(3000, 5, seed=0)
+    o = g.degree_order()
+    deg = g.degree
+    assert np.all(np.diff(o.sorted_degree) >= 0)
+    assert np.array_equal(np.sort(o.orig_of), np.arange(g.n))
+    assert np.array_equal(o.new_of[o.orig_of], np.arange(g.n))
+    assert np.array_equal(deg[o.orig_of], o.sorted_degree)
+    # relabelled adjacency is the same graph
+    for new in [0, 17, g.n - 1]:
+        nb = o.col[o.rowptr[new]:o.rowptr[new + 1]]
+        assert sorted(o.orig_of[nb].tolist()) == g.neighbors(o.orig_of[new]).tolist()
+        assert np.all(np.diff(nb) > 0)
+    assert np.all(o.sorted_degree[:o.heavy_begin] <= HEAVY_DEGREE)
+    assert np.all(o.sorted_degree[o.heavy_begin:] > HEAVY_DEGREE)
+    sup, bin_end, delta = o.support()
+    assert np.array_equal(sup, np.unique(deg)) and bin_end[-1] == g.n
+    for b in range(len(sup)):
+        assert bin_end[b] == np.sum(deg <= sup[b])
+    assert np.array_equal(delta, np.diff(sup).astype(np.float32))
+    sup0, be0, _ = o.support(include_zero=True)
+    assert sup0[0] == 0 and be0[0] == 0 and len(sup0) == len(sup) + 1
+
+
+def test_edge_insertion_and_dedup():
+    from hsd_b200.graph import CSRGraph
+    g = CSRGraph.from_edges(5, np.array([[0, 1], [1, 0], [1, 2], [3, 3]]))
+    assert g.degree.tolist() == [1, 2, 1, 1, 0]                  # duplicate collapsed, self-loop once
+    g2 = g.with_edges_added(np.array([[4, 0], [2, 1]]))
+    assert g2.degree.tolist() == [2, 2, 1, 1, 1]
+    with pytest.raises(ValueError):
+        CSRGraph.from_edges(3, np.array([[0, 3]]))
+
+
+@pytest.mark.parametrize("n,world", [(20000, 1), (20000, 8), (10, 4), (3, 8), (1190, 2)])
+def test_shard_rows_cover_every_row_once(n, world):
+    from hsd_b200.sharded import shard_rows
+    seen = []
+    for r in range(world):
+        row0, nr, per = shard_rows(n, world, r)
+        assert per * world >= n and nr <= per
+        seen += list(range(row0, row0 + nr))
+    assert seen == list(range(n))
+
+
+def test_host_pipeline_panels_tile_the_rows():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("constructor allocates device buffers; planning is exercised here on CPU only")
+    from hsd_b200.engine import HostDegreePipeline
+    for n_rows, n, full in [(20000, 20000, True), (2500, 20000, False), (100, 100, True), (129, 129, True)]:
+        p = HostDegreePipeline.__new__(HostDegreePipeline)
+        p.n_rows, p.n, p.full = n_rows, n, full
+        panels = p._plan_panels(8)
+        assert panels[0][0] == 0 and sum(r for _, r in panels) == n_rows
+        for (a, ra), (b, _) in zip(panels[:-1], panels[1:]):
+            assert a + ra == b and a % 128 == 0
+        if full and n_rows > 2000:
+            assert panels[0][1] < panels[-1][1]          # equal-work trapezoids start narrow
+
+
+def test_reference_arm_of_bench_runs_on_cpu():
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--workload", "1500x2"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["unit"] == "node-pairs/s"

@@ -270,6 +270,8 @@ extern "C" int hsd_pairwise_l1(const float* sigT, int32_t k_pad, int64_t n_pad, 
     HSD_REQUIRE(n_pad > 0 && n_pad % 4 == 0, "n_pad must be a multiple of 4");
     HSD_REQUIRE((reinterpret_cast<uintptr_t>(sigT) & 15) == 0, "sigT must be 16-byte aligned");
     HSD_REQUIRE(row0 >= 0 && col0 >= 0 && n_rows >= 0 && n_cols >= 0, "negative range");
+    // TMA tile loads start at element row0 / col0 of a K-major row: the address must be 16-byte aligned
+    HSD_REQUIRE(row0 % 4 == 0 && col0 % 4 == 0, "row0 and col0 must be multiples of 4 (16-byte TMA alignment)");
     HSD_REQUIRE(row0 + (int64_t)n_rows <= n_pad && col0 + (int64_t)n_cols <= n_pad, "range exceeds n_pad");
     HSD_REQUIRE(!symmetric || (row0 == col0 && n_cols >= n_rows), "symmetric needs row0 == col0 and n_cols >= n_rows");
     if (n_rows == 0 || n_cols == 0) return HSD_OK;

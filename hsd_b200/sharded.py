@@ -21,9 +21,10 @@ from . import engine
 
 
 def shard_rows(n: int, world: int, rank: int) -> Tuple[int, int, int]:
-    """(row0, n_rows, rows_per_rank): contiguous blocks of ceil(n / world) rows, the last
+    """(row0, n_rows, rows_per_rank): contiguous blocks of ceil(n / world) rows rounded up to
+    a multiple of 4 (the pairwise kernel's TMA tile origins must be 16-byte aligned), the last
     ranks may own fewer (or zero) rows; rows_per_rank is the all-gather chunk."""
-    per = (n + world - 1) // world
+    per = ((n + world - 1) // world + 3) // 4 * 4
     row0 = min(rank * per, n)
     return row0, max(0, min(per, n - row0)), per
 

@@ -101,7 +101,8 @@ int hsd_signature_transpose(const float* sig, int64_t sig_ld, int32_t n_rows, in
  * rows processed in order therefore complete the matrix top to bottom, which is
  * what lets the host pipeline stream finished rows out while later panels compute.
  * sigT: float[k_pad][n_pad], k_pad % HSD_PAIR_KCHUNK == 0, n_pad % 4 == 0,
- * base 16-byte aligned. Tiles are staged by TMA (cp.async.bulk.tensor.2d). */
+ * base 16-byte aligned; row0 % 4 == 0 and col0 % 4 == 0 (TMA tile origins must be
+ * 16-byte aligned). Tiles are staged by TMA (cp.async.bulk.tensor.2d). */
 int hsd_pairwise_l1(const float* sigT, int32_t k_pad, int64_t n_pad,
                     int32_t row0, int32_t n_rows, int32_t col0, int32_t n_cols,
                     int32_t symmetric, float* out, int64_t ld_out, void* stream);

@@ -30,6 +30,7 @@ def test_c_abi_argument_validation_without_gpu():
     assert lib.hsd_pairwise_l1(p, 15, 128, 0, 1, 0, 1, 0, p, 128, None) == -1     # k_pad % 16
     assert lib.hsd_pairwise_l1(p, 16, 130, 0, 1, 0, 1, 0, p, 130, None) == -1     # n_pad % 4
     assert lib.hsd_pairwise_l1(p, 16, 128, 0, 64, 0, 32, 1, p, 128, None) == -1   # symmetric trapezoid
+    assert lib.hsd_pairwise_l1(p, 16, 128, 2, 64, 0, 32, 0, p, 128, None) == -1   # TMA origin alignment
     assert lib.hsd_ring_signature_degree(None, None, 4, None, None, 1, 2, 0, None, None, 1, None, 0,
                                          None, None, 0, None, None) == -1
     assert lib.hsd_pairwise_aligned(p, p, p, 4, 2, 0, 3, 7, 0, 1, p, 4, None) == -1  # metric
@@ -109,7 +110,7 @@ def test_shard_rows_cover_every_row_once(n, world):
     seen = []
     for r in range(world):
         row0, nr, per = shard_rows(n, world, r)
-        assert per * world >= n and nr <= per
+        assert per * world >= n and nr <= per and (nr == 0 or row0 % 4 == 0)
         seen += list(range(row0, row0 + nr))
     assert seen == list(range(n))
 

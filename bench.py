@@ -240,7 +240,15 @@ def run_native(args):
     n, hops = parse_workload(args.workload)
     g = powerlaw_graph(n, 5, seed=0)       # same deterministic graph on every rank
     dg = engine.DeviceGraph.upload(g, device=dev)
-    plan = ShardedDegreeHSD(dg, hops, rank, world)
+    peer = world > 1 and not args.no_peer
+    try:
+        plan = ShardedDegreeHSD(dg, hops, rank, world, peer=peer)
+    except Exception as e:   # symmetric memory unavailable: every rank computes its full row block
+        if rank == 0:
+            print(f"[bench] peer-memory result blocks unavailable ({type(e).__name__}: {e}); "
+                  "falling back to independent row blocks", file=sys.stderr)
+        peer = False
+        plan = ShardedDegreeHSD(dg, hops, rank, world, peer=False)
     pairs = n * (n - 1) / 2
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
 
@@ -255,17 +263,10 @@ def run_native(args):
         if ev is not None:
             ev[1].record()
         plan.gather()
-        n_ = dg.n
-        engine.signature_transpose(plan.sig_all[:n_], plan.k_used, plan.sigT, 0)
         if ev is not None:
-            ev[2].record()
-        if plan.n_rows:
-            if world == 1:
-                engine.pairwise_l1(plan.sigT, n_, symmetric=True, out=plan.out)
-            else:
-                engine.pairwise_l1(plan.sigT, n_, plan.row0, plan.n_rows, 0, n_, symmetric=False, out=plan.out)
-        if ev is not None:
-            ev[3].record()
+            plan.distances(ev[2], ev[3])
+        else:
+            plan.distances()
 
     for _ in range(max(args.warmup, 0)):
         one_step()
@@ -299,6 +300,8 @@ def run_native(args):
     k_alg = plan.k_used
     if world == 1:
         launch_pairs = pairs
+    elif peer:
+        launch_pairs = pairs / world        # this rank's share of the upper-triangle tiles
     else:
         launch_pairs = plan.n_rows * n      # ordered (row, col) pairs of this rank's block
     flops = 2.0 * launch_pairs * k_alg
@@ -312,15 +315,16 @@ def run_native(args):
         "note": "tensor cores not applicable (|a-b| is not a contraction); FMA-counted peak would be 2x this",
     }
     # ---- secondary: BFS + signature kernel against HBM/L2 ----
-    sig_rows = plan.sig_all[plan.row0:plan.row0 + plan.n_rows, 1:k_alg].double()
+    own = slice(plan.rank * plan.per, plan.rank * plan.per + plan.n_src)   # this rank's BFS sources in the table
+    sig_rows = plan.sig_all[own, 1:k_alg].double()
     nb1 = dg.n_bins - 1
-    sizes = plan.sizes[plan.row0:plan.row0 + plan.n_rows].double()
+    sizes = plan.sizes[own].double()
     sup_max, sup_min = float(dg.support[-1]), float(dg.support[0])
-    edges_scanned = float((plan.sig_all[plan.row0:plan.row0 + plan.n_rows, 0].double()).sum().item())  # hop 0 expands the source
+    edges_scanned = float((plan.sig_all[own, 0].double()).sum().item())  # hop 0 expands the source
     for h in range(1, hops):   # rings 1..H-1 are expanded; sum of member degrees = n * mean = n * (max - sum_b CDF*delta)
         mean_deg = sup_max - sig_rows[:, (h - 1) * nb1:h * nb1].sum(1)
         edges_scanned += float((sizes[:, h] * mean_deg).sum().item())
-    bfs_bytes = 4.0 * edges_scanned + 4.0 * k_alg * plan.n_rows
+    bfs_bytes = 4.0 * edges_scanned + 4.0 * k_alg * plan.n_src
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -373,7 +377,12 @@ def run_native(args):
                                    + (f", row-block sharded over {world} GPUs" if world > 1 else ""),
                        "n_nodes": n, "hops": hops, "support_bins": dg.n_bins, "signature_len": k_alg,
                        "l2": "256 MB buffer written before every step (flush) + each step writes a result > L2",
-                       "symmetric": world == 1},
+                       "symmetric": world == 1 or peer,
+                       "multi_gpu": None if world == 1 else (
+                           "symmetric tiles dealt round-robin to ranks, mirrored into the owners' row blocks "
+                           "through NVLink peer memory (torch symmetric memory); one NCCL all-gather of the "
+                           "signature table" if peer else
+                           "independent row blocks (every rank computes rows x all columns); one NCCL all-gather")},
             "stage_ms": {"bfs_signature": bfs_ms, "allgather_transpose": gather_ms, "pairwise": pair_ms},
             "roofline": roofline, "roofline_bfs": roofline_bfs, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(args.steps * (3 if plan.n_rows else 2)),
@@ -392,6 +401,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-peer", action="store_true", help="N>1: independent row blocks instead of peer-memory mirroring")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -17,14 +17,18 @@ void set_error(const char* fmt, ...) {
 // sig[r][k] (row-major, ld) -> sigT[k][col0 + r] (ld n_pad); 32x32 tiles through shared memory
 __global__ void __launch_bounds__(256)
 signature_transpose_kernel(const float* __restrict__ sig, int64_t sig_ld, int n_rows, int k_used,
-                           float* __restrict__ sigT, int64_t n_pad, int col0) {
+                           float* __restrict__ sigT, int64_t n_pad, int col0,
+                           const int32_t* __restrict__ src_rows) {
     __shared__ float tile[32][33];
     const int r0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const int r = r0 + ty + q * 8, k = k0 + tx;
-        tile[ty + q * 8][tx] = (r < n_rows && k < k_used) ? sig[(int64_t)r * sig_ld + k] : 0.f;
+        // with src_rows, output column col0 + r is fed from table row src_rows[r] (a gather of
+        // whole rows: each read is still a contiguous 128-byte segment)
+        const int64_t src = (r < n_rows) ? (src_rows ? (int64_t)__ldg(src_rows + r) : (int64_t)r) : 0;
+        tile[ty + q * 8][tx] = (r < n_rows && k < k_used) ? sig[src * sig_ld + k] : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -42,7 +46,7 @@ extern "C" const char* hsd_last_error_string(void) { return hsd::g_err; }
 
 extern "C" int hsd_signature_transpose(const float* sig, int64_t sig_ld, int32_t n_rows,
                                        int32_t k_used, float* sigT, int64_t n_pad, int32_t col0,
-                                       void* stream) {
+                                       const int32_t* src_rows, void* stream) {
     using namespace hsd;
     HSD_REQUIRE(sig && sigT, "null pointer");
     HSD_REQUIRE(n_rows >= 0 && k_used >= 0 && sig_ld >= k_used, "bad sizes");
@@ -50,7 +54,7 @@ extern "C" int hsd_signature_transpose(const float* sig, int64_t sig_ld, int32_t
     if (n_rows == 0 || k_used == 0) return HSD_OK;
     dim3 grid((n_rows + 31) / 32, (k_used + 31) / 32);
     signature_transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(sig, sig_ld, n_rows, k_used,
-                                                                      sigT, n_pad, col0);
+                                                                      sigT, n_pad, col0, src_rows);
     HSD_CUDA_TRY(cudaGetLastError());
     return HSD_OK;
 }

@@ -96,7 +96,22 @@ struct PairArgs {
     float* out;
     int64_t ld;
     int vec_ok;  // float4 stores legal (ld % 4 == 0, base and col0 aligned)
+    // sharded symmetric mode: the logical N x N result lives as `world` row blocks of `per`
+    // rows, one per GPU, shard_ptrs[r] = base of block r (peer-mapped for r != this rank);
+    // this launch computes tiles tile_offset, tile_offset + tile_stride, ...
+    float* const* shard_ptrs;
+    int per;
+    int tile_stride, tile_offset;
 };
+
+// pointer to logical element (i, 0)
+__device__ __forceinline__ float* row_ptr(const PairArgs& p, int i) {
+    if (p.shard_ptrs) {
+        const int o = i / p.per;
+        return p.shard_ptrs[o] + (int64_t)(i - o * p.per) * p.ld;
+    }
+    return p.out + (int64_t)(i - p.row0) * p.ld - p.col0;
+}
 
 template <int UNROLL>
 __global__ void __launch_bounds__(PAIR_THREADS, 2)
@@ -106,7 +121,7 @@ pairwise_l1_kernel(const __grid_constant__ CUtensorMap tmap, const PairArgs p) {
 
     int I, J;
     if (p.symmetric) {
-        tri_decode(blockIdx.x, p.tiles_r, p.tiles_c, I, J);
+        tri_decode(blockIdx.x * p.tile_stride + p.tile_offset, p.tiles_r, p.tiles_c, I, J);
     } else {
         I = blockIdx.x / p.tiles_c;
         J = blockIdx.x - I * p.tiles_c;
@@ -186,7 +201,7 @@ pairwise_l1_kernel(const __grid_constant__ CUtensorMap tmap, const PairArgs p) {
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
             const int i = i_base + (r < 4 ? ty * 4 + r : 64 + ty * 4 + (r - 4));
-            float* o = p.out + (int64_t)(i - p.row0) * p.ld + (j_base - p.col0);
+            float* o = row_ptr(p, i) + j_base;
             *reinterpret_cast<float4*>(o + tx * 4) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
             *reinterpret_cast<float4*>(o + 64 + tx * 4) = make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]);
         }
@@ -194,7 +209,7 @@ pairwise_l1_kernel(const __grid_constant__ CUtensorMap tmap, const PairArgs p) {
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const int j = j_base + (q < 4 ? tx * 4 + q : 64 + tx * 4 + (q - 4));
-                float* o = p.out + (int64_t)(j - p.row0) * p.ld + (i_base - p.col0);
+                float* o = row_ptr(p, j) + i_base;
                 *reinterpret_cast<float4*>(o + ty * 4) = make_float4(acc[0][q], acc[1][q], acc[2][q], acc[3][q]);
                 *reinterpret_cast<float4*>(o + 64 + ty * 4) = make_float4(acc[4][q], acc[5][q], acc[6][q], acc[7][q]);
             }
@@ -208,9 +223,8 @@ pairwise_l1_kernel(const __grid_constant__ CUtensorMap tmap, const PairArgs p) {
             for (int q = 0; q < 8; ++q) {
                 const int j = j_base + (q < 4 ? tx * 4 + q : 64 + tx * 4 + (q - 4));
                 if (j >= col_end) continue;
-                p.out[(int64_t)(i - p.row0) * p.ld + (j - p.col0)] = acc[r][q];
-                if (p.symmetric && I != J)
-                    p.out[(int64_t)(j - p.row0) * p.ld + (i - p.col0)] = acc[r][q];
+                row_ptr(p, i)[j] = acc[r][q];
+                if (p.symmetric && I != J) row_ptr(p, j)[i] = acc[r][q];
             }
         }
     }
@@ -261,21 +275,10 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 
 }  // namespace hsd
 
-extern "C" int hsd_pairwise_l1(const float* sigT, int32_t k_pad, int64_t n_pad, int32_t row0,
-                               int32_t n_rows, int32_t col0, int32_t n_cols, int32_t symmetric,
-                               float* out, int64_t ld_out, void* stream) {
-    using namespace hsd;
-    HSD_REQUIRE(sigT && out, "null pointer");
-    HSD_REQUIRE(k_pad > 0 && k_pad % KC == 0, "k_pad must be a positive multiple of HSD_PAIR_KCHUNK");
-    HSD_REQUIRE(n_pad > 0 && n_pad % 4 == 0, "n_pad must be a multiple of 4");
-    HSD_REQUIRE((reinterpret_cast<uintptr_t>(sigT) & 15) == 0, "sigT must be 16-byte aligned");
-    HSD_REQUIRE(row0 >= 0 && col0 >= 0 && n_rows >= 0 && n_cols >= 0, "negative range");
-    // TMA tile loads start at element row0 / col0 of a K-major row: the address must be 16-byte aligned
-    HSD_REQUIRE(row0 % 4 == 0 && col0 % 4 == 0, "row0 and col0 must be multiples of 4 (16-byte TMA alignment)");
-    HSD_REQUIRE(row0 + (int64_t)n_rows <= n_pad && col0 + (int64_t)n_cols <= n_pad, "range exceeds n_pad");
-    HSD_REQUIRE(!symmetric || (row0 == col0 && n_cols >= n_rows), "symmetric needs row0 == col0 and n_cols >= n_rows");
-    if (n_rows == 0 || n_cols == 0) return HSD_OK;
+namespace hsd {
 
+static int launch_pairwise(const float* sigT, int32_t k_pad, int64_t n_pad, PairArgs a, long long n_tiles,
+                           cudaStream_t stream) {
     auto encode = get_encode();
     if (!encode) {
         set_error("cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
@@ -293,18 +296,9 @@ extern "C" int hsd_pairwise_l1(const float* sigT, int32_t k_pad, int64_t n_pad, 
         set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
         return HSD_ERR_CUDA;
     }
-
-    PairArgs a;
     a.k_chunks = k_pad / KC;
-    a.row0 = row0; a.n_rows = n_rows; a.col0 = col0; a.n_cols = n_cols;
-    a.tiles_r = (n_rows + TILE - 1) / TILE;
-    a.tiles_c = (n_cols + TILE - 1) / TILE;
-    a.symmetric = symmetric ? 1 : 0;
-    a.out = out; a.ld = ld_out;
-    a.vec_ok = (ld_out % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-    const long long n_tiles = symmetric ? (long long)a.tiles_r * a.tiles_c - (long long)a.tiles_r * (a.tiles_r - 1) / 2
-                                        : (long long)a.tiles_r * a.tiles_c;
     HSD_REQUIRE(n_tiles < (1ll << 31), "too many tiles for one launch");
+    if (n_tiles <= 0) return HSD_OK;
 
     const int smem = (int)sizeof(PairSmem);
     static int unroll = 0;   // tuning knob, read once: HSD_PAIR_UNROLL in {4, 8, 16}
@@ -314,7 +308,7 @@ extern "C" int hsd_pairwise_l1(const float* sigT, int32_t k_pad, int64_t n_pad, 
     }
     auto launch = [&](auto kern) -> int {
         HSD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        kern<<<(unsigned)n_tiles, PAIR_THREADS, smem, (cudaStream_t)stream>>>(tmap, a);
+        kern<<<(unsigned)n_tiles, PAIR_THREADS, smem, stream>>>(tmap, a);
         HSD_CUDA_TRY(cudaGetLastError());
         return HSD_OK;
     };
@@ -323,6 +317,58 @@ extern "C" int hsd_pairwise_l1(const float* sigT, int32_t k_pad, int64_t n_pad, 
         case 16: return launch(pairwise_l1_kernel<16>);
         default: return launch(pairwise_l1_kernel<8>);
     }
+}
+
+}  // namespace hsd
+
+extern "C" int hsd_pairwise_l1(const float* sigT, int32_t k_pad, int64_t n_pad, int32_t row0,
+                               int32_t n_rows, int32_t col0, int32_t n_cols, int32_t symmetric,
+                               float* out, int64_t ld_out, void* stream) {
+    using namespace hsd;
+    HSD_REQUIRE(sigT && out, "null pointer");
+    HSD_REQUIRE(k_pad > 0 && k_pad % KC == 0, "k_pad must be a positive multiple of HSD_PAIR_KCHUNK");
+    HSD_REQUIRE(n_pad > 0 && n_pad % 4 == 0, "n_pad must be a multiple of 4");
+    HSD_REQUIRE((reinterpret_cast<uintptr_t>(sigT) & 15) == 0, "sigT must be 16-byte aligned");
+    HSD_REQUIRE(row0 >= 0 && col0 >= 0 && n_rows >= 0 && n_cols >= 0, "negative range");
+    // TMA tile loads start at element row0 / col0 of a K-major row: the address must be 16-byte aligned
+    HSD_REQUIRE(row0 % 4 == 0 && col0 % 4 == 0, "row0 and col0 must be multiples of 4 (16-byte TMA alignment)");
+    HSD_REQUIRE(row0 + (int64_t)n_rows <= n_pad && col0 + (int64_t)n_cols <= n_pad, "range exceeds n_pad");
+    HSD_REQUIRE(!symmetric || (row0 == col0 && n_cols >= n_rows), "symmetric needs row0 == col0 and n_cols >= n_rows");
+    if (n_rows == 0 || n_cols == 0) return HSD_OK;
+    PairArgs a = {};
+    a.row0 = row0; a.n_rows = n_rows; a.col0 = col0; a.n_cols = n_cols;
+    a.tiles_r = (n_rows + TILE - 1) / TILE;
+    a.tiles_c = (n_cols + TILE - 1) / TILE;
+    a.symmetric = symmetric ? 1 : 0;
+    a.out = out; a.ld = ld_out;
+    a.vec_ok = (ld_out % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    a.shard_ptrs = nullptr; a.per = 1; a.tile_stride = 1; a.tile_offset = 0;
+    const long long n_tiles = symmetric ? (long long)a.tiles_r * a.tiles_c - (long long)a.tiles_r * (a.tiles_r - 1) / 2
+                                        : (long long)a.tiles_r * a.tiles_c;
+    return launch_pairwise(sigT, k_pad, n_pad, a, n_tiles, (cudaStream_t)stream);
+}
+
+extern "C" int hsd_pairwise_l1_sharded(const float* sigT, int32_t k_pad, int64_t n_pad, int32_t n_nodes,
+                                       int32_t rank, int32_t world, int32_t rows_per_rank,
+                                       float* const* shard_ptrs, int64_t ld_out, void* stream) {
+    using namespace hsd;
+    HSD_REQUIRE(sigT && shard_ptrs, "null pointer");
+    HSD_REQUIRE(k_pad > 0 && k_pad % KC == 0, "k_pad must be a positive multiple of HSD_PAIR_KCHUNK");
+    HSD_REQUIRE(n_pad > 0 && n_pad % 4 == 0 && n_nodes > 0 && n_nodes <= n_pad, "bad n_pad / n_nodes");
+    HSD_REQUIRE((reinterpret_cast<uintptr_t>(sigT) & 15) == 0, "sigT must be 16-byte aligned");
+    HSD_REQUIRE(world >= 1 && rank >= 0 && rank < world, "bad rank / world");
+    HSD_REQUIRE(rows_per_rank > 0 && (int64_t)rows_per_rank * world >= n_nodes, "row blocks do not cover the matrix");
+    HSD_REQUIRE(ld_out >= n_nodes && ld_out % 4 == 0, "ld_out must be >= n_nodes and a multiple of 4");
+    PairArgs a = {};
+    a.row0 = 0; a.n_rows = n_nodes; a.col0 = 0; a.n_cols = n_nodes;
+    a.tiles_r = a.tiles_c = (n_nodes + TILE - 1) / TILE;
+    a.symmetric = 1;
+    a.out = nullptr; a.ld = ld_out;
+    a.vec_ok = 1;   // block bases come from the allocator (>= 256-byte aligned), ld_out % 4 == 0
+    a.shard_ptrs = shard_ptrs; a.per = rows_per_rank; a.tile_stride = world; a.tile_offset = rank;
+    const long long total = (long long)a.tiles_r * (a.tiles_r + 1) / 2;
+    const long long mine = total > rank ? (total - rank + world - 1) / world : 0;
+    return launch_pairwise(sigT, k_pad, n_pad, a, mine, (cudaStream_t)stream);
 }
 
 extern "C" int hsd_fp32_peak_probe(float* sink, int32_t iters, int64_t* lane_ops_host, void* stream) {

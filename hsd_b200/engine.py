@@ -145,9 +145,12 @@ def alloc_signature_table(k_used: int, n: int, device) -> torch.Tensor:
     return torch.zeros((k_pad, n_pad), dtype=torch.float32, device=device)
 
 
-def signature_transpose(sig: torch.Tensor, k_used: int, sigT: torch.Tensor, col0: int = 0) -> None:
-    check(lib.hsd_signature_transpose(_ptr(sig), sig.stride(0), sig.shape[0], k_used,
-                                      _ptr(sigT), sigT.stride(0), col0, _stream()))
+def signature_transpose(sig: torch.Tensor, k_used: int, sigT: torch.Tensor, col0: int = 0,
+                        src_rows: Optional[torch.Tensor] = None) -> None:
+    """sigT[k, col0 + r] = sig[src_rows[r] if src_rows is given else r, k]."""
+    n_rows = sig.shape[0] if src_rows is None else int(src_rows.numel())
+    check(lib.hsd_signature_transpose(_ptr(sig), sig.stride(0), n_rows, k_used,
+                                      _ptr(sigT), sigT.stride(0), col0, _ptr(src_rows), _stream()))
 
 
 def pairwise_l1(sigT: torch.Tensor, n: int, row0: int = 0, n_rows: Optional[int] = None,

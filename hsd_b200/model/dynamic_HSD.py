@@ -125,7 +125,7 @@ class DynamicHSD(MultiHSD):
             n4 = engine.roundup(n, 4)
             sigT = engine.alloc_signature_table(k_used, n4 + m, sig.device)
             engine.signature_transpose(sig, k_used, sigT, 0)
-            engine.signature_transpose(sig[aff].contiguous(), k_used, sigT, n4)
+            engine.signature_transpose(sig, k_used, sigT, n4, src_rows=aff.to(torch.int32).contiguous())
             blk = engine.pairwise_l1(sigT, n4 + m, row0=n4, n_rows=m, col0=0, n_cols=n, symmetric=False)
             self._D[aff, :] = blk
             self._D[:, aff] = blk.t()

@@ -33,7 +33,12 @@ class ShardedDegreeHSD:
     """Plan + buffers for repeated evaluation of one graph on `world` ranks."""
 
     def __init__(self, dg: engine.DeviceGraph, hops: int, rank: int = 0, world: int = 1,
-                 group=None, empty: str = "raise"):
+                 group=None, empty: str = "raise", peer: bool = False, peer_blocks=None):
+        """peer=True (world > 1): the result blocks are allocated as symmetric memory and mapped
+        into every rank over NVLink; the pairwise kernel then computes each symmetric tile once
+        in the whole job and stores its mirror straight into the owner's block
+        (hsd_pairwise_l1_sharded).  peer=False: every rank computes its full row block.
+        peer_blocks: list of `world` local tensors standing in for the peers' blocks (tests)."""
         self.dg, self.hops, self.rank, self.world, self.group, self.empty = dg, hops, rank, world, group, empty
         n = dg.n
         dev = dg.rowptr.device
@@ -43,24 +48,50 @@ class ShardedDegreeHSD:
         # row-major signature table, padded to world * per rows so every rank's chunk is equal
         self.sig_all = torch.zeros((world * self.per, self.ld), dtype=torch.float32, device=dev)
         self.sigT = engine.alloc_signature_table(self.k_used, n, dev)
-        self.rows = torch.arange(self.row0, self.row0 + self.n_rows, dtype=torch.int32, device=dev)
+        # BFS sources are DEALT round-robin (node s -> rank s % world): contiguous blocks would give
+        # one rank all the hubs of a preferential-attachment graph (its BFS then takes 2x longer).
+        # Table row of node s in the gathered table: (s % world) * per + s // world.
+        self.rows = torch.arange(rank, n, world, dtype=torch.int32, device=dev)
+        self.n_src = int(self.rows.numel())
         self.src = dg.new_of[self.rows.long()].contiguous()
-        self.out_rows = torch.arange(self.row0, self.row0 + self.n_rows, dtype=torch.int32, device=dev)
+        self.out_rows = (rank * self.per + torch.arange(self.n_src, dtype=torch.int32, device=dev)).contiguous()
+        node = torch.arange(n, dtype=torch.int32, device=dev)
+        self.table_row = ((node % world) * self.per + node // world).to(torch.int32).contiguous()
         self.sizes = torch.zeros((world * self.per, hops + 1), dtype=torch.int32, device=dev)
         self.status = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.out = torch.empty((max(self.n_rows, 1), n), dtype=torch.float32, device=dev)
         self.launches_per_step = 3
+        self.peer = bool(peer) and world > 1
+        self.symm = None
+        self.ld_out = engine.roundup(n, 4)
+        if self.peer and peer_blocks is not None:
+            self.blocks = peer_blocks
+            self.out_full = peer_blocks[rank]
+            self.ptrs = torch.tensor([b.data_ptr() for b in peer_blocks], dtype=torch.int64, device=dev)
+        elif self.peer:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm_mem
+            self.out_full = symm_mem.empty((self.per, self.ld_out), dtype=torch.float32, device=dev)
+            self.symm = symm_mem.rendezvous(self.out_full, group if group is not None else dist.group.WORLD)
+            self.ptrs = torch.tensor([int(p) for p in self.symm.buffer_ptrs], dtype=torch.int64, device=dev)
+        if self.peer:
+            self.out = self.out_full[:max(self.n_rows, 1), :n]
+        else:
+            self.out = torch.empty((max(self.n_rows, 1), n), dtype=torch.float32, device=dev)
+
+    def ring_sizes(self) -> torch.Tensor:
+        """int32[N, hops+1] in node order (valid after gather for world > 1 only for own sources)."""
+        return self.sizes[self.table_row.long()] if self.world > 1 else self.sizes[:self.dg.n]
 
     def signatures(self) -> None:
         """BFS + degree CDF for this rank's sources, written straight into its slice of the
         gathered table."""
         from ._lib import check, lib
         dg = self.dg
-        if self.n_rows == 0:
+        if self.n_src == 0:
             return
         check(lib.hsd_ring_signature_degree(
             engine._ptr(dg.rowptr), engine._ptr(dg.col), dg.n, engine._ptr(self.src),
-            engine._ptr(self.out_rows), self.n_rows, self.hops, dg.heavy_begin,
+            engine._ptr(self.out_rows), self.n_src, self.hops, dg.heavy_begin,
             engine._ptr(dg.bin_end), engine._ptr(dg.delta), dg.n_bins,
             engine._ptr(self.sig_all), self.ld, engine._ptr(self.sizes), None,
             1 if self.empty == "zero" else 0, engine._ptr(self.status), engine._stream()))
@@ -73,15 +104,41 @@ class ShardedDegreeHSD:
         chunk = self.sig_all[self.rank * self.per:(self.rank + 1) * self.per]
         dist.all_gather_into_tensor(self.sig_all, chunk, group=self.group)
 
-    def distances(self) -> torch.Tensor:
+    def distances(self, ev_before=None, ev_after=None) -> torch.Tensor:
+        """Transpose the gathered table to K-major and run the pairwise kernel; the optional
+        CUDA events bracket the pairwise launch alone (bench.py's roofline timing)."""
+        out = self._distances(ev_before)
+        if ev_after is not None:
+            ev_after.record()
+        if self.peer:
+            self.peer_barrier()
+        return out
+
+    def _distances(self, ev_before) -> torch.Tensor:
         n = self.dg.n
-        engine.signature_transpose(self.sig_all, self.k_used, self.sigT, 0) if n == self.sig_all.shape[0] else \
-            engine.signature_transpose(self.sig_all[:n], self.k_used, self.sigT, 0)
+        engine.signature_transpose(self.sig_all, self.k_used, self.sigT, 0,
+                                   src_rows=None if self.world == 1 else self.table_row)
+        if ev_before is not None:
+            ev_before.record()
+        if self.peer:
+            from ._lib import check, lib
+            check(lib.hsd_pairwise_l1_sharded(engine._ptr(self.sigT), self.sigT.shape[0], self.sigT.stride(0),
+                                              n, self.rank, self.world, self.per, engine._ptr(self.ptrs),
+                                              self.ld_out, engine._stream()))
+            return self.out[:self.n_rows]
         if self.n_rows == 0:
             return self.out[:0]
         if self.world == 1:
             return engine.pairwise_l1(self.sigT, n, symmetric=True, out=self.out)
         return engine.pairwise_l1(self.sigT, n, self.row0, self.n_rows, 0, n, symmetric=False, out=self.out)
+
+    def peer_barrier(self) -> None:
+        """A block is complete only when every rank's launch has stored its tiles into it."""
+        if self.symm is not None:
+            self.symm.barrier()
+        elif self.world > 1 and not hasattr(self, "blocks"):
+            import torch.distributed as dist
+            dist.barrier(group=self.group)
 
     def step(self) -> torch.Tensor:
         self.signatures()

@@ -83,11 +83,14 @@ int hsd_bfs_rings(const int32_t* rowptr, const int32_t* col, int32_t n_nodes,
                   int32_t* ring_sizes, uint32_t* ring_bitmaps, void* stream);
 
 /* ---- layout: row-major signatures -> K-major table for the pairwise kernel --
- * sig[n_rows][sig_ld] (first k_used columns) -> sigT[k_pad][n_pad] at column
- * offset col0; rows k_used..k_pad-1 and columns beyond the data must be zero
- * (caller memsets sigT once). */
+ * sig[.][sig_ld] (first k_used columns) -> sigT[k_pad][n_pad]: output column
+ * col0 + r (r < n_rows) is table row r, or table row src_rows[r] when src_rows is
+ * given (the multi-GPU plan deals BFS sources round-robin to ranks for balance, so
+ * the gathered table is in dealt order).  Rows k_used..k_pad-1 and columns beyond
+ * the data must be zero (caller memsets sigT once). */
 int hsd_signature_transpose(const float* sig, int64_t sig_ld, int32_t n_rows, int32_t k_used,
-                            float* sigT, int64_t n_pad, int32_t col0, void* stream);
+                            float* sigT, int64_t n_pad, int32_t col0, const int32_t* src_rows,
+                            void* stream);
 
 /* ---- K3: pairwise L1 over the K-major signature table ----------------------
  * Replaces the O(N^2 (H+1)) scipy loop model/HSD.py:103-112 (and :144-159).
@@ -106,6 +109,21 @@ int hsd_signature_transpose(const float* sig, int64_t sig_ld, int32_t n_rows, in
 int hsd_pairwise_l1(const float* sigT, int32_t k_pad, int64_t n_pad,
                     int32_t row0, int32_t n_rows, int32_t col0, int32_t n_cols,
                     int32_t symmetric, float* out, int64_t ld_out, void* stream);
+
+/* ---- K3 over several GPUs: symmetric tiles, mirrored through peer memory ------
+ * The logical N x N matrix is row-block sharded: block r = float[rows_per_rank][ld_out]
+ * in GPU r's memory, shard_ptrs[r] (a DEVICE array of `world` pointers) its base as
+ * mapped into THIS process (own allocation for r == rank, NVLink peer mapping
+ * otherwise).  Rank `rank` computes upper-triangle tiles rank, rank+world, ... of the
+ * whole matrix and stores each tile to the owner of its rows AND, mirrored, to the
+ * owner of its columns with plain st.global on the peer pointers — so no tile is
+ * computed twice anywhere in the job and the N(N-1)/2 pairs cost the same FADDs on
+ * G GPUs as on one.  Block r is complete once every rank's launch has finished
+ * (the caller issues one barrier).  The reference mirrors dist_mat[i,j] = dist_mat[j,i]
+ * the same way (model/HSD.py:112). */
+int hsd_pairwise_l1_sharded(const float* sigT, int32_t k_pad, int64_t n_pad, int32_t n_nodes,
+                            int32_t rank, int32_t world, int32_t rows_per_rank,
+                            float* const* shard_ptrs, int64_t ld_out, void* stream);
 
 /* ---- K2 (value mode): ring gather + sort ----------------------------------
  * Replaces model/HSD.py:71-83 (get_hierarchical_coeffcients) plus the argsort

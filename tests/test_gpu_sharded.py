@@ -21,11 +21,41 @@ def test_emulated_ranks_equal_single_gpu(world):
         p.signatures()
     for p in plans:                       # emulate the in-place all-gather
         for q in plans:
-            p.sig_all[q.row0:q.row0 + q.n_rows] = q.sig_all[q.row0:q.row0 + q.n_rows]
+            sl = slice(q.rank * q.per, q.rank * q.per + q.n_src)
+            p.sig_all[sl] = q.sig_all[sl]
     blocks = [p.distances() for p in plans]
     torch.cuda.synchronize()
     assert torch.equal(torch.cat(blocks, 0), single)
     assert sum(p.n_rows for p in plans) == g.n
+
+
+@pytest.mark.parametrize("world,n", [(2, 2500), (4, 1801)])
+def test_emulated_peer_memory_symmetric_tiles(world, n):
+    """hsd_pairwise_l1_sharded with the peers' blocks standing in as local buffers: every
+    rank's launch writes direct + mirrored tiles into the owners' blocks; after all launches
+    the blocks hold exactly the single-GPU matrix."""
+    import torch
+    from hsd_b200 import engine
+    from hsd_b200.graph import powerlaw_graph
+    from hsd_b200.sharded import ShardedDegreeHSD, shard_rows
+    g = powerlaw_graph(n, 5, seed=0)
+    dg = engine.DeviceGraph.upload(g)
+    single = ShardedDegreeHSD(dg, 3, 0, 1).step().clone()
+    per = shard_rows(n, world, 0)[2]
+    ld = engine.roundup(n, 4)
+    blocks = [torch.full((per, ld), float("nan"), dtype=torch.float32, device="cuda") for _ in range(world)]
+    plans = [ShardedDegreeHSD(dg, 3, r, world, peer=True, peer_blocks=blocks) for r in range(world)]
+    for p in plans:
+        p.signatures()
+    for p in plans:
+        for q in plans:
+            sl = slice(q.rank * q.per, q.rank * q.per + q.n_src)
+            p.sig_all[sl] = q.sig_all[sl]
+    for p in plans:
+        p.distances()
+    torch.cuda.synchronize()
+    got = torch.cat([b[:, :n] for b in blocks], 0)[:n]
+    assert torch.equal(got, single)
 
 
 def test_host_pipeline_matches_device_path():

@@ -141,3 +141,18 @@ def test_reference_arm_of_bench_runs_on_cpu():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["unit"] == "node-pairs/s"
+
+
+def test_product_package_never_touches_the_oracle_or_reference():
+    """oracle/ is test infrastructure: nothing under hsd_b200/, model/ or tools/ may import it,
+    and nothing shipped may read /root/reference."""
+    import glob
+    bad = []
+    for path in glob.glob(os.path.join(ROOT, "hsd_b200", "**", "*.py"), recursive=True) + \
+            glob.glob(os.path.join(ROOT, "model", "*.py")) + glob.glob(os.path.join(ROOT, "tools", "*.py")):
+        src = open(path).read()
+        if re.search(r"^\s*(from|import)\s+oracle\b", src, re.M) or "/root/reference" in src:
+            bad.append(path)
+    assert not bad, bad
+    for path in [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")]:
+        assert "/root/reference" not in open(path).read()

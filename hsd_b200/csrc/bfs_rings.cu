@@ -20,6 +20,8 @@
 namespace hsd {
 
 constexpr int BFS_THREADS = 256;
+constexpr int FL_CAP = 2048;                       // frontier nodes expanded per round
+constexpr int FL_PER_THREAD = FL_CAP / BFS_THREADS;
 
 struct BfsArgs {
     const int32_t* rowptr;
@@ -30,7 +32,6 @@ struct BfsArgs {
     const int32_t* out_rows;
     int32_t n_src;
     int32_t hops;
-    int32_t heavy_word_begin;
     const int32_t* bin_end;
     const float* delta;
     int32_t n_bins;
@@ -50,16 +51,27 @@ __device__ __forceinline__ void visit_neighbor(int u, const uint32_t* __restrict
     if (!((V[w] | *((volatile uint32_t*)&Fn[w])) & m)) atomicOr(&Fn[w], m);
 }
 
+// One CTA per source.  Shared memory: visited V, two ring bitmaps (ping-pong), the prefix
+// popcount P of the current ring, and a FL_CAP-entry frontier list (CSR start + edge prefix).
+//
+// Expansion is EDGE-balanced: the frontier ring is compacted (its prefix popcount gives every
+// member its slot), the degrees are scanned, and each thread walks an equal, contiguous share
+// of the concatenated adjacency lists.  A node-per-thread / node-per-warp split left most of the
+// CTA waiting at the level barrier behind the few threads that drew the hubs (ncu r1: 50 % of
+// all stall samples on that barrier).
 __global__ void __launch_bounds__(BFS_THREADS)
 bfs_ring_signature_kernel(const BfsArgs p) {
     extern __shared__ uint32_t bfs_smem[];
     __shared__ int warp_tot[BFS_THREADS / 32];
+    __shared__ int fl_start[FL_CAP];
+    __shared__ int fl_eo[FL_CAP + 1];
 
     const int nw = p.n_words;
     uint32_t* V = bfs_smem;
-    uint32_t* F = V + nw;
-    uint32_t* Fn = F + nw;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t* R0 = V + nw;
+    uint32_t* R1 = R0 + nw;
+    uint32_t* P = R1 + nw;
+    const int tid = threadIdx.x;
     const int hops1 = p.hops + 1;
     const int nb1 = p.n_bins - 1;
 
@@ -68,53 +80,95 @@ bfs_ring_signature_kernel(const BfsArgs p) {
     const int s = p.src_nodes[sidx];
     const int64_t row = p.out_rows[sidx];
 
-    for (int w = tid; w < nw; w += BFS_THREADS) { V[w] = 0u; F[w] = 0u; }
-    __syncthreads();
+    // ---- hop 0: the ring is the source alone ----
+    for (int w = tid; w < nw; w += BFS_THREADS) {
+        const uint32_t b = (w == (s >> 5)) ? (1u << (s & 31)) : 0u;
+        V[w] = b;
+        R0[w] = b;
+        P[w] = (w > (s >> 5)) ? 1u : 0u;
+    }
     if (tid == 0) {
-        V[s >> 5] = 1u << (s & 31);
-        F[s >> 5] = 1u << (s & 31);
         if (p.ring_sizes) p.ring_sizes[row * hops1] = 1;
-        // hop 0: the ring is the source alone; its W1 term is |deg_i - deg_j|.
+        // its W1 term is |deg_i - deg_j|: one scalar instead of a CDF
         if (p.sig) p.sig[row * p.sig_ld] = (float)(p.rowptr[s + 1] - p.rowptr[s]);
     }
     __syncthreads();
     if (p.ring_bitmaps) {
         uint32_t* dst = p.ring_bitmaps + (row * hops1) * (int64_t)nw;
-        for (int w = tid; w < nw; w += BFS_THREADS) dst[w] = F[w];
+        for (int w = tid; w < nw; w += BFS_THREADS) dst[w] = R0[w];
     }
 
-    // words per thread for the prefix-popcount pass (contiguous chunks)
-    const int cpt = (nw + BFS_THREADS - 1) / BFS_THREADS;
+    const int cpt = (nw + BFS_THREADS - 1) / BFS_THREADS;  // words per thread, prefix-popcount pass
+    int n_cur = 1;
 
     for (int h = 1; h <= p.hops; ++h) {
+        uint32_t* F = (h & 1) ? R0 : R1;    // ring h-1 (prefix popcounts in P)
+        uint32_t* Fn = (h & 1) ? R1 : R0;   // ring h
         for (int w = tid; w < nw; w += BFS_THREADS) Fn[w] = 0u;
         __syncthreads();
 
-        // ---- expand: light nodes, one thread per frontier node -------------
-        for (int w = tid; w < p.heavy_word_begin; w += BFS_THREADS) {
-            uint32_t bits = F[w];
-            while (bits) {
-                const int v = (w << 5) + __ffs(bits) - 1;
-                bits &= bits - 1;
-                const int e1 = __ldg(p.rowptr + v + 1);
-                for (int e = __ldg(p.rowptr + v); e < e1; ++e)
-                    visit_neighbor(__ldg(p.col + e), V, Fn);
+        for (int r0 = 0; r0 < n_cur; r0 += FL_CAP) {
+            const int m = min(FL_CAP, n_cur - r0);
+            // ---- compact ring members with rank in [r0, r0 + m) into the frontier list ----
+            for (int w = tid; w < nw; w += BFS_THREADS) {
+                uint32_t bits = F[w];
+                if (!bits) continue;
+                int pos = (int)P[w] - r0;
+                if (pos >= m || pos + __popc(bits) <= 0) continue;
+                while (bits) {
+                    const int v = (w << 5) + __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    if (pos >= 0 && pos < m) {
+                        const int e0 = __ldg(p.rowptr + v);
+                        fl_start[pos] = e0;
+                        fl_eo[pos] = __ldg(p.rowptr + v + 1) - e0;   // degree for now
+                    }
+                    ++pos;
+                }
             }
-        }
-        // ---- expand: heavy nodes, one warp per frontier node ----------------
-        for (int w = p.heavy_word_begin + warp; w < nw; w += BFS_THREADS / 32) {
-            uint32_t bits = F[w];
-            while (bits) {
-                const int v = (w << 5) + __ffs(bits) - 1;
-                bits &= bits - 1;
-                const int e1 = __ldg(p.rowptr + v + 1);
-                for (int e = __ldg(p.rowptr + v) + lane; e < e1; e += 32)
-                    visit_neighbor(__ldg(p.col + e), V, Fn);
+            __syncthreads();
+            // ---- exclusive scan of the degrees -> edge offsets ----
+            int loc[FL_PER_THREAD];
+            int sum = 0;
+#pragma unroll
+            for (int q = 0; q < FL_PER_THREAD; ++q) {
+                const int i = tid * FL_PER_THREAD + q;
+                loc[q] = (i < m) ? fl_eo[i] : 0;
+                sum += loc[q];
             }
+            int total;
+            int run = block_exclusive_scan<BFS_THREADS>(sum, warp_tot, &total);   // syncs inside
+#pragma unroll
+            for (int q = 0; q < FL_PER_THREAD; ++q) {
+                const int i = tid * FL_PER_THREAD + q;
+                if (i < m) fl_eo[i] = run;
+                run += loc[q];
+            }
+            if (tid == 0) fl_eo[m] = total;
+            __syncthreads();
+            // ---- each thread walks an equal contiguous share of the `total` edges ----
+            const int share = (total + BFS_THREADS - 1) / BFS_THREADS;
+            int e = min(tid * share, total);
+            const int e_hi = min(e + share, total);
+            if (e < e_hi) {
+                int lo = 0, hi = m;             // largest k in [0, m) with fl_eo[k] <= e
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (fl_eo[mid] <= e) lo = mid; else hi = mid;
+                }
+                int k = lo;
+                while (e < e_hi) {
+                    const int k_end = min(fl_eo[k + 1], e_hi);
+                    const int32_t* cp = p.col + fl_start[k] + (e - fl_eo[k]);
+#pragma unroll 4
+                    for (; e < k_end; ++e, ++cp) visit_neighbor(__ldg(cp), V, Fn);
+                    ++k;
+                }
+            }
+            __syncthreads();
         }
-        __syncthreads();
 
-        // ---- ring h = Fn: visited |= ring; prefix popcount into F (dead) ----
+        // ---- ring h = Fn: visited |= ring; prefix popcount into P ----
         const int w_lo = min(tid * cpt, nw), w_hi = min(w_lo + cpt, nw);
         int local = 0;
         for (int w = w_lo; w < w_hi; ++w) local += __popc(Fn[w]);
@@ -122,7 +176,7 @@ bfs_ring_signature_kernel(const BfsArgs p) {
         int run = block_exclusive_scan<BFS_THREADS>(local, warp_tot, &n_ring);
         for (int w = w_lo; w < w_hi; ++w) {
             const uint32_t r = Fn[w];
-            F[w] = (uint32_t)run;
+            P[w] = (uint32_t)run;
             run += __popc(r);
             V[w] |= r;
         }
@@ -139,7 +193,7 @@ bfs_ring_signature_kernel(const BfsArgs p) {
                 const float n_f = (float)n_ring;
                 for (int b = tid; b < nb1; b += BFS_THREADS) {
                     const int e = __ldg(p.bin_end + b);  // < n_nodes for b < n_bins-1
-                    const int cnt = (int)F[e >> 5] + __popc(Fn[e >> 5] & ((1u << (e & 31)) - 1u));
+                    const int cnt = (int)P[e >> 5] + __popc(Fn[e >> 5] & ((1u << (e & 31)) - 1u));
                     // integer count times integer gap, then one IEEE divide (<= 1.5 ulp total)
                     dst[b] = __fdiv_rn((float)cnt * __ldg(p.delta + b), n_f);
                 }
@@ -150,17 +204,18 @@ bfs_ring_signature_kernel(const BfsArgs p) {
                     dst[b] = p.empty_as_zero ? __ldg(p.delta + b) : 0.f;
             }
         }
-        __syncthreads();
-        uint32_t* t = F; F = Fn; Fn = t;
+        n_cur = n_ring;
+        // no barrier needed here: the next level's first barrier orders these reads of P / Fn
+        // before anything overwrites them (Fn of level h+1 is the buffer F of this level)
     }
 }
 
 static int launch_bfs(const BfsArgs& a, cudaStream_t stream) {
     if (a.n_src == 0) return HSD_OK;
-    const size_t smem = (size_t)3 * a.n_words * sizeof(uint32_t);
+    const size_t smem = (size_t)4 * a.n_words * sizeof(uint32_t);
     if (smem > 200 * 1024) {
         set_error("hsd_bfs: %d nodes need %zu B of bitmap shared memory (> 200 KB); "
-                  "graphs above ~540k nodes are not supported by this kernel", a.n_nodes, smem);
+                  "graphs above ~400k nodes are not supported by this kernel", a.n_nodes, smem);
         return HSD_ERR_UNSUPPORTED;
     }
     HSD_CUDA_TRY(cudaFuncSetAttribute(bfs_ring_signature_kernel,
@@ -189,7 +244,6 @@ extern "C" int hsd_ring_signature_degree(const int32_t* rowptr, const int32_t* c
     hsd::BfsArgs a;
     a.rowptr = rowptr; a.col = col; a.n_nodes = n_nodes; a.n_words = (n_nodes + 31) / 32;
     a.src_nodes = src_nodes; a.out_rows = out_rows; a.n_src = n_src; a.hops = hops;
-    a.heavy_word_begin = heavy_begin / 32;
     a.bin_end = bin_end; a.delta = delta; a.n_bins = sig ? n_bins : 1;
     a.sig = sig; a.sig_ld = sig_ld; a.ring_sizes = ring_sizes; a.ring_bitmaps = ring_bitmaps;
     a.empty_as_zero = empty_as_zero; a.status = status;

@@ -19,13 +19,11 @@
 
 namespace hsd {
 
-constexpr int BFS_THREADS = 256;
 constexpr int FL_CAP = 2048;                       // frontier nodes expanded per round
-constexpr int FL_PER_THREAD = FL_CAP / BFS_THREADS;
 
 struct BfsArgs {
     const int32_t* rowptr;
-    const int32_t* col;
+    const int32_t* col;                            // readable up to the next multiple of 4 entries
     int32_t n_nodes;
     int32_t n_words;
     const int32_t* src_nodes;
@@ -43,32 +41,39 @@ struct BfsArgs {
     int32_t* status;
 };
 
-__device__ __forceinline__ void visit_neighbor(int u, const uint32_t* __restrict__ V,
-                                               uint32_t* __restrict__ Fn) {
+// `seen` = every node discovered so far (all earlier rings + the part of the current ring found
+// so far).  One plain read filters the common case; a new node costs two shared-memory atomics.
+__device__ __forceinline__ void visit_neighbor(int u, uint32_t* __restrict__ seen,
+                                               uint32_t* __restrict__ ring) {
     const uint32_t m = 1u << (u & 31);
     const int w = u >> 5;
-    // Fn is read racily on purpose: a stale 0 only costs a redundant atomicOr.
-    if (!((V[w] | *((volatile uint32_t*)&Fn[w])) & m)) atomicOr(&Fn[w], m);
+    if (!(*((volatile uint32_t*)&seen[w]) & m)) {
+        if (!(atomicOr(&seen[w], m) & m)) atomicOr(&ring[w], m);
+    }
 }
 
-// One CTA per source.  Shared memory: visited V, two ring bitmaps (ping-pong), the prefix
+// One CTA per source.  Shared memory: the `seen` bitmap, two ring bitmaps (ping-pong), the prefix
 // popcount P of the current ring, and a FL_CAP-entry frontier list (CSR start + edge prefix).
 //
 // Expansion is EDGE-balanced: the frontier ring is compacted (its prefix popcount gives every
 // member its slot), the degrees are scanned, and each thread walks an equal, contiguous share
-// of the concatenated adjacency lists.  A node-per-thread / node-per-warp split left most of the
-// CTA waiting at the level barrier behind the few threads that drew the hubs (ncu r1: 50 % of
-// all stall samples on that barrier).
-__global__ void __launch_bounds__(BFS_THREADS)
+// of the concatenated adjacency lists with 16-byte loads (4 column indices per LDG.128, masked at
+// the ends of a node's list).  A node-per-thread / node-per-warp split left most of the CTA
+// waiting at the level barrier behind the few threads that drew the hubs (ncu r1: 50 % of all
+// stall samples on that barrier); scalar 4-byte loads relied on L1 keeping each 32-byte sector
+// alive across 8 iterations and re-fetched it 4x from L2 instead (59 % L1 hit rate).
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
 bfs_ring_signature_kernel(const BfsArgs p) {
+    constexpr int FL_PER_THREAD = FL_CAP / THREADS;
     extern __shared__ uint32_t bfs_smem[];
-    __shared__ int warp_tot[BFS_THREADS / 32];
+    __shared__ int warp_tot[THREADS / 32];
     __shared__ int fl_start[FL_CAP];
     __shared__ int fl_eo[FL_CAP + 1];
 
     const int nw = p.n_words;
-    uint32_t* V = bfs_smem;
-    uint32_t* R0 = V + nw;
+    uint32_t* S = bfs_smem;
+    uint32_t* R0 = S + nw;
     uint32_t* R1 = R0 + nw;
     uint32_t* P = R1 + nw;
     const int tid = threadIdx.x;
@@ -81,9 +86,9 @@ bfs_ring_signature_kernel(const BfsArgs p) {
     const int64_t row = p.out_rows[sidx];
 
     // ---- hop 0: the ring is the source alone ----
-    for (int w = tid; w < nw; w += BFS_THREADS) {
+    for (int w = tid; w < nw; w += THREADS) {
         const uint32_t b = (w == (s >> 5)) ? (1u << (s & 31)) : 0u;
-        V[w] = b;
+        S[w] = b;
         R0[w] = b;
         P[w] = (w > (s >> 5)) ? 1u : 0u;
     }
@@ -95,22 +100,22 @@ bfs_ring_signature_kernel(const BfsArgs p) {
     __syncthreads();
     if (p.ring_bitmaps) {
         uint32_t* dst = p.ring_bitmaps + (row * hops1) * (int64_t)nw;
-        for (int w = tid; w < nw; w += BFS_THREADS) dst[w] = R0[w];
+        for (int w = tid; w < nw; w += THREADS) dst[w] = R0[w];
     }
 
-    const int cpt = (nw + BFS_THREADS - 1) / BFS_THREADS;  // words per thread, prefix-popcount pass
+    const int cpt = (nw + THREADS - 1) / THREADS;  // words per thread, prefix-popcount pass
     int n_cur = 1;
 
     for (int h = 1; h <= p.hops; ++h) {
         uint32_t* F = (h & 1) ? R0 : R1;    // ring h-1 (prefix popcounts in P)
         uint32_t* Fn = (h & 1) ? R1 : R0;   // ring h
-        for (int w = tid; w < nw; w += BFS_THREADS) Fn[w] = 0u;
+        for (int w = tid; w < nw; w += THREADS) Fn[w] = 0u;
         __syncthreads();
 
         for (int r0 = 0; r0 < n_cur; r0 += FL_CAP) {
             const int m = min(FL_CAP, n_cur - r0);
             // ---- compact ring members with rank in [r0, r0 + m) into the frontier list ----
-            for (int w = tid; w < nw; w += BFS_THREADS) {
+            for (int w = tid; w < nw; w += THREADS) {
                 uint32_t bits = F[w];
                 if (!bits) continue;
                 int pos = (int)P[w] - r0;
@@ -137,7 +142,7 @@ bfs_ring_signature_kernel(const BfsArgs p) {
                 sum += loc[q];
             }
             int total;
-            int run = block_exclusive_scan<BFS_THREADS>(sum, warp_tot, &total);   // syncs inside
+            int run = block_exclusive_scan<THREADS>(sum, warp_tot, &total);   // syncs inside
 #pragma unroll
             for (int q = 0; q < FL_PER_THREAD; ++q) {
                 const int i = tid * FL_PER_THREAD + q;
@@ -147,7 +152,7 @@ bfs_ring_signature_kernel(const BfsArgs p) {
             if (tid == 0) fl_eo[m] = total;
             __syncthreads();
             // ---- each thread walks an equal contiguous share of the `total` edges ----
-            const int share = (total + BFS_THREADS - 1) / BFS_THREADS;
+            const int share = (total + THREADS - 1) / THREADS;
             int e = min(tid * share, total);
             const int e_hi = min(e + share, total);
             if (e < e_hi) {
@@ -158,40 +163,48 @@ bfs_ring_signature_kernel(const BfsArgs p) {
                 }
                 int k = lo;
                 while (e < e_hi) {
+                    const int eo_k = fl_eo[k];
                     const int k_end = min(fl_eo[k + 1], e_hi);
-                    const int32_t* cp = p.col + fl_start[k] + (e - fl_eo[k]);
-#pragma unroll 4
-                    for (; e < k_end; ++e, ++cp) visit_neighbor(__ldg(cp), V, Fn);
+                    const int base = fl_start[k] - eo_k;     // CSR index = base + e
+                    int i = base + e;
+                    const int i_end = base + k_end;
+                    // aligned 16-byte groups; entries outside [i, i_end) are masked
+                    for (int g = i & ~3; g < i_end; g += 4) {
+                        const int4 c = __ldg(reinterpret_cast<const int4*>(p.col + g));
+                        if (g >= i && g < i_end) visit_neighbor(c.x, S, Fn);
+                        if (g + 1 >= i && g + 1 < i_end) visit_neighbor(c.y, S, Fn);
+                        if (g + 2 >= i && g + 2 < i_end) visit_neighbor(c.z, S, Fn);
+                        if (g + 3 >= i && g + 3 < i_end) visit_neighbor(c.w, S, Fn);
+                    }
+                    e = k_end;
                     ++k;
                 }
             }
             __syncthreads();
         }
 
-        // ---- ring h = Fn: visited |= ring; prefix popcount into P ----
+        // ---- ring h = Fn: prefix popcount into P ----
         const int w_lo = min(tid * cpt, nw), w_hi = min(w_lo + cpt, nw);
         int local = 0;
         for (int w = w_lo; w < w_hi; ++w) local += __popc(Fn[w]);
         int n_ring;
-        int run = block_exclusive_scan<BFS_THREADS>(local, warp_tot, &n_ring);
+        int run = block_exclusive_scan<THREADS>(local, warp_tot, &n_ring);
         for (int w = w_lo; w < w_hi; ++w) {
-            const uint32_t r = Fn[w];
             P[w] = (uint32_t)run;
-            run += __popc(r);
-            V[w] |= r;
+            run += __popc(Fn[w]);
         }
         __syncthreads();
 
         if (tid == 0 && p.ring_sizes) p.ring_sizes[row * hops1 + h] = n_ring;
         if (p.ring_bitmaps) {
             uint32_t* dst = p.ring_bitmaps + (row * hops1 + h) * (int64_t)nw;
-            for (int w = tid; w < nw; w += BFS_THREADS) dst[w] = Fn[w];
+            for (int w = tid; w < nw; w += THREADS) dst[w] = Fn[w];
         }
         if (p.sig) {
             float* dst = p.sig + row * p.sig_ld + 1 + (int64_t)(h - 1) * nb1;
             if (n_ring > 0) {
                 const float n_f = (float)n_ring;
-                for (int b = tid; b < nb1; b += BFS_THREADS) {
+                for (int b = tid; b < nb1; b += THREADS) {
                     const int e = __ldg(p.bin_end + b);  // < n_nodes for b < n_bins-1
                     const int cnt = (int)P[e >> 5] + __popc(Fn[e >> 5] & ((1u << (e & 31)) - 1u));
                     // integer count times integer gap, then one IEEE divide (<= 1.5 ulp total)
@@ -200,7 +213,7 @@ bfs_ring_signature_kernel(const BfsArgs p) {
             } else {
                 if (!p.empty_as_zero && tid == 0) atomicOr(p.status, 1);
                 // empty ring == point mass at 0 (zero padding of tools/metrics.py:18-36): CDF = 1
-                for (int b = tid; b < nb1; b += BFS_THREADS)
+                for (int b = tid; b < nb1; b += THREADS)
                     dst[b] = p.empty_as_zero ? __ldg(p.delta + b) : 0.f;
             }
         }
@@ -218,9 +231,16 @@ static int launch_bfs(const BfsArgs& a, cudaStream_t stream) {
                   "graphs above ~400k nodes are not supported by this kernel", a.n_nodes, smem);
         return HSD_ERR_UNSUPPORTED;
     }
-    HSD_CUDA_TRY(cudaFuncSetAttribute(bfs_ring_signature_kernel,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bfs_ring_signature_kernel<<<a.n_src, BFS_THREADS, smem, stream>>>(a);
+    // large graphs: the bitmaps limit an SM to a few CTAs, so use 512-thread CTAs to keep warps resident
+    if (a.n_nodes > 48 * 1024) {
+        HSD_CUDA_TRY(cudaFuncSetAttribute(bfs_ring_signature_kernel<512>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        bfs_ring_signature_kernel<512><<<a.n_src, 512, smem, stream>>>(a);
+    } else {
+        HSD_CUDA_TRY(cudaFuncSetAttribute(bfs_ring_signature_kernel<256>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        bfs_ring_signature_kernel<256><<<a.n_src, 256, smem, stream>>>(a);
+    }
     HSD_CUDA_TRY(cudaGetLastError());
     return HSD_OK;
 }

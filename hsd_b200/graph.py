@@ -24,7 +24,7 @@ class DegreeOrder:
     orig_of: np.ndarray      # int32[N]  new id -> original index
     new_of: np.ndarray       # int32[N]  original index -> new id
     rowptr: np.ndarray       # int32[N+1]
-    col: np.ndarray          # int32[nnz]
+    col: np.ndarray          # int32[nnz padded to a multiple of 4 (+4)]: LDG.128 reads in the BFS kernel
     heavy_begin: int         # first new id with degree > HEAVY_DEGREE
     sorted_degree: np.ndarray  # int32[N] degree of new id
 
@@ -101,9 +101,12 @@ class CSRGraph:
             sdeg = deg[orig_of]
             rowptr = np.zeros(self.n + 1, dtype=np.int32)
             np.cumsum(sdeg, out=rowptr[1:])
+            col = (key % self.n).astype(np.int32)
+            # the BFS kernel reads column indices in aligned groups of 4 (LDG.128): pad the tail
+            col = np.concatenate([col, np.zeros((-len(col)) % 4 + 4, dtype=np.int32)])
             self._order = DegreeOrder(
                 orig_of=orig_of, new_of=new_of, rowptr=rowptr,
-                col=(key % self.n).astype(np.int32),
+                col=col,
                 heavy_begin=int(np.searchsorted(sdeg, HEAVY_DEGREE, side="right")),
                 sorted_degree=sdeg.astype(np.int32))
         return self._order

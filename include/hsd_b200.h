@@ -55,10 +55,11 @@ const char* hsd_last_error_string(void);
  * such rows == sum over hops of the 1-D Wasserstein-1 distance between the
  * degree multisets of the rings.
  *
- *   rowptr[n_nodes+1], col[nnz]   CSR, degree-ascending node order
+ *   rowptr[n_nodes+1], col[nnz]   CSR, degree-ascending node order; col must be 16-byte aligned and
+ *                                 readable up to the next multiple of 4 entries (it is read with LDG.128)
  *   src_nodes[n_src]              sources (ids in that order)
  *   out_rows[n_src]               row of sig / ring_sizes / ring_bitmaps each source writes
- *   heavy_begin                   first node id handled warp-cooperatively (degree > threshold)
+ *   heavy_begin                   reserved (ignored since the expansion became edge-balanced)
  *   bin_end[n_bins]               # nodes with degree <= support[b]  (== first id of bin b+1)
  *   delta[n_bins-1]               support[b+1]-support[b]
  *   sig (nullable)                float[rows][sig_ld], sig_ld >= 1 + hops*(n_bins-1)

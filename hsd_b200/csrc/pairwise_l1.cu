@@ -113,8 +113,11 @@ __device__ __forceinline__ float* row_ptr(const PairArgs& p, int i) {
     return p.out + (int64_t)(i - p.row0) * p.ld - p.col0;
 }
 
+#ifndef HSD_PAIR_MINB
+#define HSD_PAIR_MINB 2
+#endif
 template <int UNROLL>
-__global__ void __launch_bounds__(PAIR_THREADS, 2)
+__global__ void __launch_bounds__(PAIR_THREADS, HSD_PAIR_MINB)
 pairwise_l1_kernel(const __grid_constant__ CUtensorMap tmap, const PairArgs p) {
     extern __shared__ __align__(128) unsigned char pair_smem_raw[];
     PairSmem& sm = *reinterpret_cast<PairSmem*>(pair_smem_raw);
@@ -179,16 +182,50 @@ pairwise_l1_kernel(const __grid_constant__ CUtensorMap tmap, const PairArgs p) {
         // (ncu: stall_no_instruction 0.82 -> 0.09 per issue, profiles/r1_pairwise_notes.md).
 #pragma unroll UNROLL
         for (int kk = 0; kk < KC; ++kk) {
+#ifndef HSD_PAIR_VARIANT
+#define HSD_PAIR_VARIANT 2
+#endif
+#if HSD_PAIR_VARIANT == 3 || HSD_PAIR_VARIANT == 4
+            // 64-bit operand loads: register pairs instead of aligned quads give ptxas more freedom
+            const float2 a00 = *reinterpret_cast<const float2*>(&sm.a[s][kk][ty * 4]);
+            const float2 a01 = *reinterpret_cast<const float2*>(&sm.a[s][kk][ty * 4 + 2]);
+            const float2 a10 = *reinterpret_cast<const float2*>(&sm.a[s][kk][64 + ty * 4]);
+            const float2 a11 = *reinterpret_cast<const float2*>(&sm.a[s][kk][64 + ty * 4 + 2]);
+            const float2 b00 = *reinterpret_cast<const float2*>(&sm.b[s][kk][tx * 4]);
+            const float2 b01 = *reinterpret_cast<const float2*>(&sm.b[s][kk][tx * 4 + 2]);
+            const float2 b10 = *reinterpret_cast<const float2*>(&sm.b[s][kk][64 + tx * 4]);
+            const float2 b11 = *reinterpret_cast<const float2*>(&sm.b[s][kk][64 + tx * 4 + 2]);
+            const float av[8] = {a00.x, a00.y, a01.x, a01.y, a10.x, a10.y, a11.x, a11.y};
+            const float bv[8] = {b00.x, b00.y, b01.x, b01.y, b10.x, b10.y, b11.x, b11.y};
+#else
             const float4 a0 = *reinterpret_cast<const float4*>(&sm.a[s][kk][ty * 4]);
             const float4 a1 = *reinterpret_cast<const float4*>(&sm.a[s][kk][64 + ty * 4]);
             const float4 b0 = *reinterpret_cast<const float4*>(&sm.b[s][kk][tx * 4]);
             const float4 b1 = *reinterpret_cast<const float4*>(&sm.b[s][kk][64 + tx * 4]);
             const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
             const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#endif
+#if HSD_PAIR_VARIANT == 1 || HSD_PAIR_VARIANT == 4
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+#pragma unroll
+                for (int r = 0; r < 8; ++r) acc[r][q] += fabsf(av[r] - bv[q]);
+#elif HSD_PAIR_VARIANT == 2
+            float d[8][8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) d[r][q] = av[r] - bv[q];
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) acc[r][q] += fabsf(d[r][q]);
+#else
 #pragma unroll
             for (int r = 0; r < 8; ++r)
 #pragma unroll
                 for (int q = 0; q < 8; ++q) acc[r][q] += fabsf(av[r] - bv[q]);
+#endif
         }
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(smem_u32(&sm.empty[s]));

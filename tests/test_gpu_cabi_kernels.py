@@ -1,0 +1,145 @@
+"""Kernel-level parity through the C-ABI on synthetic tables and random graphs: edge sizes
+(N not a multiple of the tile, tiny K, rectangular and trapezoid ranges), ragged / empty
+rings, disconnected graphs, self-loops."""
+import numpy as np
+import pytest
+
+from oracle import hsd_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _l1_ref(T, rows, cols):
+    # integer-valued floats: every partial sum is exact in fp32, so equality is bit-exact
+    return np.abs(T[:, rows][:, :, None] - T[:, cols][:, None, :]).sum(0)
+
+
+@pytest.mark.parametrize("n,k", [(1, 1), (5, 3), (127, 16), (128, 17), (129, 33), (300, 100), (1000, 7)])
+def test_pairwise_l1_symmetric_exact(n, k):
+    import torch
+    from hsd_b200 import engine
+    rng = np.random.default_rng(n * 1000 + k)
+    T = rng.integers(0, 50, size=(k, n)).astype(np.float32)
+    sigT = engine.alloc_signature_table(k, n, "cuda")
+    sigT[:k, :n] = torch.from_numpy(T).cuda()
+    D = engine.pairwise_l1(sigT, n, symmetric=True).cpu().numpy()
+    ref = _l1_ref(T.astype(np.float64), np.arange(n), np.arange(n))
+    assert np.array_equal(D, ref)
+
+
+@pytest.mark.parametrize("n,k,r0,nr,c0,nc", [(500, 40, 0, 500, 0, 500), (500, 40, 128, 200, 0, 500),
+                                            (777, 9, 4, 129, 256, 300), (260, 5, 256, 4, 0, 260)])
+def test_pairwise_l1_rectangles_exact(n, k, r0, nr, c0, nc):
+    import torch
+    from hsd_b200 import engine
+    rng = np.random.default_rng(7)
+    T = rng.integers(-20, 20, size=(k, n)).astype(np.float32)
+    sigT = engine.alloc_signature_table(k, n, "cuda")
+    sigT[:k, :n] = torch.from_numpy(T).cuda()
+    D = engine.pairwise_l1(sigT, n, r0, nr, c0, nc, symmetric=False).cpu().numpy()
+    assert np.array_equal(D, _l1_ref(T.astype(np.float64), np.arange(r0, r0 + nr), np.arange(c0, c0 + nc)))
+
+
+def test_pairwise_l1_trapezoid_panels_compose_the_matrix():
+    import torch
+    from hsd_b200 import engine
+    from hsd_b200._lib import check, lib
+    n, k = 700, 21
+    rng = np.random.default_rng(3)
+    T = rng.integers(0, 9, size=(k, n)).astype(np.float32)
+    sigT = engine.alloc_signature_table(k, n, "cuda")
+    sigT[:k, :n] = torch.from_numpy(T).cuda()
+    D = torch.full((n, n), -1.0, dtype=torch.float32, device="cuda")
+    for p0, pr in [(0, 128), (128, 256), (384, 316)]:
+        view = D[p0:, p0:]
+        check(lib.hsd_pairwise_l1(sigT.data_ptr(), sigT.shape[0], sigT.stride(0), p0, pr, p0, n - p0, 1,
+                                  view.data_ptr(), D.stride(0), torch.cuda.current_stream().cuda_stream))
+    assert np.array_equal(D.cpu().numpy(), _l1_ref(T.astype(np.float64), np.arange(n), np.arange(n)))
+
+
+def test_signature_transpose_with_row_gather():
+    import torch
+    from hsd_b200 import engine
+    rng = np.random.default_rng(0)
+    sig = torch.from_numpy(rng.random((300, 44)).astype(np.float32)).cuda()
+    perm = torch.from_numpy(rng.permutation(300).astype(np.int32)).cuda()
+    sigT = engine.alloc_signature_table(41, 300, "cuda")
+    engine.signature_transpose(sig, 41, sigT, 0, src_rows=perm)
+    assert torch.equal(sigT[:41, :300], sig[perm.long(), :41].t())
+    assert torch.all(sigT[41:] == 0)
+
+
+def _random_graph(rng, n, m, self_loops=0):
+    from hsd_b200.graph import CSRGraph
+    e = rng.integers(0, n, size=(m, 2))
+    if self_loops:
+        s = rng.integers(0, n, size=self_loops)
+        e = np.concatenate([e, np.stack([s, s], 1)])
+    return CSRGraph.from_edges(n, e)
+
+
+@pytest.mark.parametrize("n,m,hops,loops", [(40, 30, 3, 0), (200, 150, 4, 5), (513, 2000, 2, 0), (64, 0, 2, 0), (90, 300, 6, 3)])
+def test_bfs_rings_on_random_graphs(n, m, hops, loops):
+    """Disconnected components, isolated nodes, self-loops, rings that run empty."""
+    import torch
+    from hsd_b200 import engine
+    rng = np.random.default_rng(n + m)
+    g = _random_graph(rng, n, m, loops)
+    dg = engine.DeviceGraph.upload(g, include_zero=True)
+    sig, sizes, bitmaps, status = engine.ring_signature_degree(dg, hops, want_bitmaps=True, empty="zero")
+    bm = bitmaps.cpu().numpy().view(np.uint32)
+    bits = np.unpackbits(bm.view(np.uint8), axis=-1, bitorder="little")[..., :n]
+    orig = g.degree_order().orig_of
+    adj = [g.neighbors(i).astype(np.int64) for i in range(n)]
+    ref = O.all_rings(adj, hops)
+    for i in range(n):
+        got = [sorted(orig[np.nonzero(bits[i, h])[0]].tolist()) for h in range(hops + 1)]
+        assert got == ref[i]
+        assert sizes[i].tolist() == [len(l) for l in ref[i]]
+    # signatures -> distances, empty rings as the point mass at 0
+    k = dg.k_used(hops)
+    sigT = engine.alloc_signature_table(k, n, sig.device)
+    engine.signature_transpose(sig, k, sigT)
+    D = engine.pairwise_l1(sigT, n, symmetric=True).cpu().numpy().astype(np.float64)
+    rows = list(range(0, n, max(1, n // 12)))
+    want = O.degree_distance_rows(adj, hops, rows, empty="zero")
+    np.testing.assert_allclose(D[rows], want, rtol=1e-5, atol=1e-6 * max(want.max(), 1.0))
+
+
+def test_value_mode_kernels_on_ragged_signals():
+    """hsd_ring_signature_values + hsd_pairwise_w1_merge / _aligned against scipy on random
+    signals (negative values, ties, rings of very different sizes)."""
+    import torch
+    from hsd_b200 import engine, rings
+    rng = np.random.default_rng(11)
+    g = _random_graph(rng, 60, 140)
+    n = g.n
+    dg = engine.DeviceGraph.upload(g)
+    rs = rings.RingSet.bfs(dg, 2)
+    psi = np.round(rng.standard_normal((n, n)), 1)          # ties on purpose
+    psi_d = torch.from_numpy(psi).cuda()
+    adj = [g.neighbors(i).astype(np.int64) for i in range(n)]
+    ref_rings = O.all_rings(adj, 2)
+    vals, offs = rings.sorted_ring_values(psi_d, rs)
+    vals, offs = vals.cpu().numpy(), offs.cpu().numpy()
+    for i in [0, 13, 59]:
+        for h in range(3):
+            want = np.sort(psi[i, ref_rings[i][h]])
+            got = vals[offs[i * 3 + h]:offs[i * 3 + h + 1]]
+            assert np.array_equal(got, want)
+    empties = any(len(ref_rings[i][h]) == 0 for i in range(n) for h in range(3))
+    Da = rings.value_distance(psi_d, rs, mode="aligned", metric="wasserstein").cpu().numpy()
+    Dh = rings.value_distance(psi_d, rs, mode="aligned", metric="hellinger").cpu().numpy()
+    for i, j in [(0, 1), (5, 40), (22, 59)]:
+        wa = sum(O.aligned_distance(list(psi[i, ref_rings[i][h]]), list(psi[j, ref_rings[j][h]]), "wasserstein") for h in range(3))
+        wh = sum(O.aligned_distance(list(psi[i, ref_rings[i][h]]), list(psi[j, ref_rings[j][h]]), "hellinger") for h in range(3))
+        assert Da[i, j] == pytest.approx(wa, rel=1e-12, abs=1e-14) and Da[j, i] == Da[i, j]
+        assert Dh[i, j] == pytest.approx(wh, rel=1e-12, abs=1e-14)
+    if empties:
+        with pytest.raises(ValueError):
+            rings.value_distance(psi_d, rs, mode="w1")
+    else:
+        Dw = rings.value_distance(psi_d, rs, mode="w1").cpu().numpy()
+        for i, j in [(0, 1), (5, 40), (22, 59)]:
+            ww = sum(O.w1(psi[i, ref_rings[i][h]], psi[j, ref_rings[j][h]]) for h in range(3))
+            assert Dw[i, j] == pytest.approx(ww, rel=1e-12, abs=1e-14)

@@ -306,9 +306,17 @@ def run_native(args):
         launch_pairs = plan.n_rows * n      # ordered (row, col) pairs of this rank's block
     flops = 2.0 * launch_pairs * k_alg
     achieved = flops / (pair_ms * 1e-3) / 1e12 if pair_ms > 0 else 0.0
+    traffic = None   # DRAM bytes per launch from the committed ncu --set full capture of this workload
+    try:
+        with open(os.path.join(ROOT, "profiles", "pairwise_ncu_traffic.json")) as f:
+            cap = json.load(f)
+        if world == 1 and cap.get("workload") == args.workload:
+            traffic = cap["dram_bytes_read"] + cap["dram_bytes_write"]
+    except Exception:
+        pass
     roofline = {
         "kernel": "pairwise_l1_kernel", "bound": "fp32", "achieved": achieved, "peak": fp32_peak / 1e12,
-        "unit": "TFLOP/s", "frac": achieved / (fp32_peak / 1e12), "traffic": None,
+        "unit": "TFLOP/s", "frac": achieved / (fp32_peak / 1e12), "traffic": traffic,
         "peak_source": "measured live: hsd_fp32_peak_probe (register-only FADD sub+|.|-accumulate), "
                        "1 flop per lane per clock; MEASURED_PEAKS.json has no FP32 CUDA-core entry",
         "flops_per_launch": flops, "ms_per_launch": pair_ms,

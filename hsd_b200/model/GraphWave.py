@@ -1,7 +1,8 @@
 """Drop-in for ``model/GraphWave.py`` (class GraphWave, :10-69) — the component
 adjacent to the hot path (SURVEY.md §8 f rank 1).  Wavelets come from the same
 device paths as HSD (Chebyshev SpMM kernel, order 40, threshold 1e-5/N here);
-the characteristic-function sampling is a plain torch reduction for now."""
+the characteristic-function sampling is the fused sincos reduction kernel
+hsd_characteristic_function."""
 from __future__ import annotations
 
 import networkx as nx
@@ -52,9 +53,16 @@ class GraphWave(object):
         return self._characteristic(x, sample_points)[0].cpu().numpy()
 
     def _characteristic(self, rows: torch.Tensor, sample_points) -> torch.Tensor:
-        t = torch.as_tensor(np.asarray(sample_points, dtype=np.float64), device=self.device)
-        ang = rows[:, None, :] * t[None, :, None]
-        return torch.stack([torch.cos(ang).mean(-1), torch.sin(ang).mean(-1)], dim=-1).reshape(rows.shape[0], -1)
+        from .._lib import check, lib
+        t = torch.as_tensor(np.asarray(sample_points, dtype=np.float64), device=self.device).contiguous()
+        rows = rows.contiguous()
+        out = torch.empty((rows.shape[0], 2 * t.numel()), dtype=torch.float64, device=self.device)
+        for r0 in range(0, rows.shape[0], 32768):
+            blk = rows[r0:r0 + 32768]
+            check(lib.hsd_characteristic_function(engine._ptr(blk), blk.stride(0), blk.shape[0], blk.shape[1],
+                                                  engine._ptr(t), t.numel(), engine._ptr(out[r0:r0 + 32768]),
+                                                  engine._stream()))
+        return out
 
     def embed(self, sample_points):
         assert self.wavelets is not None, "GraphWave wavelets is None!"

@@ -207,6 +207,13 @@ int hsd_ring_reduce(const double* psiT, int32_t n_scales, int32_t n_nodes, int32
                     const uint32_t* ring_bitmaps, const int32_t* ring_sizes,
                     const int32_t* orig_of, int32_t hops, int32_t col0, double* emb, void* stream);
 
+/* ---- K6: GraphWave characteristic-function embedding --------------------------
+ * Replaces model/GraphWave.py:53-69: out[i][2k], out[i][2k+1] = Re, Im of
+ * mean_j exp(i * sample_points[k] * psi[i][j]), j < n_cols.  FP64, deterministic.
+ *   psi double[n_rows][psi_ld], sample_points double[n_points] (device), out double[n_rows][2*n_points] */
+int hsd_characteristic_function(const double* psi, int64_t psi_ld, int32_t n_rows, int32_t n_cols,
+                                const double* sample_points, int32_t n_points, double* out, void* stream);
+
 /* ---- measurement helper: FP32 CUDA-core issue peak ---------------------------
  * Runs a register-only FADD kernel (same sub + |.|-accumulate instruction mix as
  * the pairwise inner loop, no memory) and returns lane-ops in *lane_ops; the

@@ -5,16 +5,13 @@
 // ring signals, the sort + searchsorted inside scipy.stats.wasserstein_distance
 // as called from model/HSD.py:103-112.
 //
-// Design: one CTA per source; visited / frontier / next-frontier
-// are N-bit bitmaps in shared memory (3*N/8 bytes: 37.5 KB at N = 100k).  Node
-// ids are in degree-ascending order, which buys three things at once:
-//   * the ring's degree CDF at support[b] is popcount(ring bitmap[0:bin_end[b]))
-//     -> one block prefix-popcount per ring, no histogram atomics;
-//   * "light" nodes (degree <= threshold) form a prefix of the id space and are
-//     expanded one thread per node with near-uniform trip counts inside a warp
-//     (neighbouring ids have neighbouring degrees);
-//   * "heavy" nodes form the suffix and are expanded warp-cooperatively with
-//     coalesced 128-byte reads of their adjacency lists.
+// Design: one CTA per source; the `seen` set, two ring bitmaps and the ring's
+// prefix popcount live in shared memory (4 * N/8 bytes: 50 KB at N = 100k).  Node ids are in
+// degree-ascending order, so the ring's degree CDF at support[b] is
+// popcount(ring bitmap[0 : bin_end[b])) -> one block prefix-popcount per ring and NO histogram
+// atomics (the skewed degree distribution would serialise them).  The same prefix popcount gives
+// every ring member its slot in a compact frontier list, which is expanded edge-balanced.
+#include <stdlib.h>
 #include "hsd_common.cuh"
 
 namespace hsd {
@@ -231,8 +228,16 @@ static int launch_bfs(const BfsArgs& a, cudaStream_t stream) {
                   "graphs above ~400k nodes are not supported by this kernel", a.n_nodes, smem);
         return HSD_ERR_UNSUPPORTED;
     }
-    // large graphs: the bitmaps limit an SM to a few CTAs, so use 512-thread CTAs to keep warps resident
-    if (a.n_nodes > 48 * 1024) {
+    // large graphs: the bitmaps limit an SM to a few CTAs, so use 512-thread CTAs to keep warps resident;
+    // small graphs: per-level fixed costs (barriers, scans) dominate, so use small CTAs and more of them
+    static int force = -1;   // tuning knob: HSD_BFS_THREADS in {128, 256, 512}
+    if (force < 0) { const char* e = getenv("HSD_BFS_THREADS"); force = e ? atoi(e) : 0; }
+    const int threads = force ? force : (a.n_nodes > 48 * 1024 ? 512 : 256);
+    if (threads == 128) {
+        HSD_CUDA_TRY(cudaFuncSetAttribute(bfs_ring_signature_kernel<128>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        bfs_ring_signature_kernel<128><<<a.n_src, 128, smem, stream>>>(a);
+    } else if (threads == 512) {
         HSD_CUDA_TRY(cudaFuncSetAttribute(bfs_ring_signature_kernel<512>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         bfs_ring_signature_kernel<512><<<a.n_src, 512, smem, stream>>>(a);
@@ -249,14 +254,13 @@ static int launch_bfs(const BfsArgs& a, cudaStream_t stream) {
 
 extern "C" int hsd_ring_signature_degree(const int32_t* rowptr, const int32_t* col, int32_t n_nodes,
                                          const int32_t* src_nodes, const int32_t* out_rows,
-                                         int32_t n_src, int32_t hops, int32_t heavy_begin,
+                                         int32_t n_src, int32_t hops,
                                          const int32_t* bin_end, const float* delta, int32_t n_bins,
                                          float* sig, int64_t sig_ld, int32_t* ring_sizes,
                                          uint32_t* ring_bitmaps, int32_t empty_as_zero,
                                          int32_t* status, void* stream) {
     HSD_REQUIRE(rowptr && col && src_nodes && out_rows, "null graph/source pointer");
     HSD_REQUIRE(n_nodes > 0 && n_src >= 0 && hops >= 0, "bad sizes");
-    HSD_REQUIRE(heavy_begin >= 0 && heavy_begin <= n_nodes, "heavy_begin out of range");
     if (sig) {
         HSD_REQUIRE(bin_end && delta && n_bins >= 1 && status, "sig requested without support tables");
         HSD_REQUIRE(sig_ld >= 1 + (int64_t)hops * (n_bins - 1), "sig_ld too small");
@@ -272,9 +276,9 @@ extern "C" int hsd_ring_signature_degree(const int32_t* rowptr, const int32_t* c
 
 extern "C" int hsd_bfs_rings(const int32_t* rowptr, const int32_t* col, int32_t n_nodes,
                              const int32_t* src_nodes, const int32_t* out_rows, int32_t n_src,
-                             int32_t hops, int32_t heavy_begin, int32_t* ring_sizes,
+                             int32_t hops, int32_t* ring_sizes,
                              uint32_t* ring_bitmaps, void* stream) {
     return hsd_ring_signature_degree(rowptr, col, n_nodes, src_nodes, out_rows, n_src, hops,
-                                     heavy_begin, nullptr, nullptr, 1, nullptr, 0, ring_sizes,
+                                     nullptr, nullptr, 1, nullptr, 0, ring_sizes,
                                      ring_bitmaps, 1, nullptr, stream);
 }

@@ -57,7 +57,6 @@ class DeviceGraph:
     col: torch.Tensor
     orig_of: torch.Tensor      # int32[N] new id -> original index
     new_of: torch.Tensor       # int32[N]
-    heavy_begin: int
     bin_end: torch.Tensor      # int32[B]
     delta: torch.Tensor        # float32[max(B-1,1)]
     n_bins: int
@@ -77,7 +76,7 @@ class DeviceGraph:
             return torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=non_blocking)
 
         return cls(n=g.n, rowptr=up(o.rowptr), col=up(o.col) if o.col.size else torch.zeros(1, dtype=torch.int32, device=dev),
-                   orig_of=up(o.orig_of), new_of=up(o.new_of), heavy_begin=o.heavy_begin,
+                   orig_of=up(o.orig_of), new_of=up(o.new_of),
                    bin_end=up(bin_end), delta=up(delta), n_bins=int(sup.size), support=sup,
                    include_zero=include_zero)
 
@@ -129,7 +128,7 @@ def ring_signature_degree(dg: DeviceGraph, hops: int, rows: Optional[torch.Tenso
     status = torch.zeros(1, dtype=torch.int32, device=dev)
     check(lib.hsd_ring_signature_degree(
         _ptr(dg.rowptr), _ptr(dg.col), dg.n, _ptr(src), _ptr(out_rows), n_src, hops,
-        dg.heavy_begin, _ptr(dg.bin_end), _ptr(dg.delta), dg.n_bins,
+        _ptr(dg.bin_end), _ptr(dg.delta), dg.n_bins,
         _ptr(sig), ld, _ptr(sizes), _ptr(bitmaps), 1 if empty == "zero" else 0,
         _ptr(status), _stream()))
     return sig, sizes, bitmaps, status
@@ -243,7 +242,6 @@ class HostDegreePipeline:
             delta = np.zeros(1, dtype=np.float32)
         self.n = g.n
         self.n_bins = int(sup.size)
-        self.heavy_begin = o.heavy_begin
         self.host = {k: _pin(v) for k, v in dict(rowptr=o.rowptr, col=o.col if o.col.size else np.zeros(1, np.int32),
                                                  orig_of=o.orig_of, new_of=o.new_of, bin_end=bin_end,
                                                  delta=delta).items()}
@@ -292,7 +290,7 @@ class HostDegreePipeline:
         self.status.zero_()
         check(lib.hsd_ring_signature_degree(
             _ptr(d["rowptr"]), _ptr(d["col"]), self.n, _ptr(d["new_of"]), _ptr(self.out_rows_idx), self.n,
-            self.hops, self.heavy_begin, _ptr(d["bin_end"]), _ptr(d["delta"]), self.n_bins,
+            self.hops, _ptr(d["bin_end"]), _ptr(d["delta"]), self.n_bins,
             _ptr(self.sig), self.sig.stride(0), None, None, 1 if self.empty == "zero" else 0,
             _ptr(self.status), _stream()))
         signature_transpose(self.sig, self.k_used, self.sigT, 0)

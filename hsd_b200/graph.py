@@ -14,9 +14,6 @@ from typing import Hashable, List, Optional, Sequence
 
 import numpy as np
 
-# nodes with more neighbours than this are expanded one warp per node by the BFS kernel
-HEAVY_DEGREE = 32
-
 
 @dataclass
 class DegreeOrder:
@@ -25,7 +22,6 @@ class DegreeOrder:
     new_of: np.ndarray       # int32[N]  original index -> new id
     rowptr: np.ndarray       # int32[N+1]
     col: np.ndarray          # int32[nnz padded to a multiple of 4 (+4)]: LDG.128 reads in the BFS kernel
-    heavy_begin: int         # first new id with degree > HEAVY_DEGREE
     sorted_degree: np.ndarray  # int32[N] degree of new id
 
     def support(self, include_zero: bool = False):
@@ -107,7 +103,6 @@ class CSRGraph:
             self._order = DegreeOrder(
                 orig_of=orig_of, new_of=new_of, rowptr=rowptr,
                 col=col,
-                heavy_begin=int(np.searchsorted(sdeg, HEAVY_DEGREE, side="right")),
                 sorted_degree=sdeg.astype(np.int32))
         return self._order
 

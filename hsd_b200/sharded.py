@@ -91,7 +91,7 @@ class ShardedDegreeHSD:
             return
         check(lib.hsd_ring_signature_degree(
             engine._ptr(dg.rowptr), engine._ptr(dg.col), dg.n, engine._ptr(self.src),
-            engine._ptr(self.out_rows), self.n_src, self.hops, dg.heavy_begin,
+            engine._ptr(self.out_rows), self.n_src, self.hops,
             engine._ptr(dg.bin_end), engine._ptr(dg.delta), dg.n_bins,
             engine._ptr(self.sig_all), self.ld, engine._ptr(self.sizes), None,
             1 if self.empty == "zero" else 0, engine._ptr(self.status), engine._stream()))

@@ -47,8 +47,11 @@ const char* hsd_last_error_string(void);
  * and, in degree mode, the per-ring sort inside
  * scipy.stats.wasserstein_distance as called from model/HSD.py:103-112.
  *
- * One CTA per source.  visited / frontier / next-frontier are N-bit bitmaps in
- * shared memory.  For hop h = 1..hops the ring bitmap is turned into
+ * One CTA per source.  The seen set, the ring bitmaps and the ring's prefix
+ * popcount are N-bit / N/32-word arrays in shared memory; the frontier ring is
+ * compacted and expanded edge-balanced (every thread walks an equal share of the
+ * concatenated adjacency lists with 16-byte loads).  For hop h = 1..hops the ring
+ * bitmap is turned into
  *   sig[row][1 + (h-1)*(n_bins-1) + b] = CDF_h(support[b]) * (support[b+1]-support[b])
  * for b = 0..n_bins-2, and sig[row][0] = degree(source) (the hop-0 ring is the
  * source alone, so its W1 term is |deg_i - deg_j|).  L1 distance between two
@@ -59,7 +62,6 @@ const char* hsd_last_error_string(void);
  *                                 readable up to the next multiple of 4 entries (it is read with LDG.128)
  *   src_nodes[n_src]              sources (ids in that order)
  *   out_rows[n_src]               row of sig / ring_sizes / ring_bitmaps each source writes
- *   heavy_begin                   reserved (ignored since the expansion became edge-balanced)
  *   bin_end[n_bins]               # nodes with degree <= support[b]  (== first id of bin b+1)
  *   delta[n_bins-1]               support[b+1]-support[b]
  *   sig (nullable)                float[rows][sig_ld], sig_ld >= 1 + hops*(n_bins-1)
@@ -71,7 +73,7 @@ const char* hsd_last_error_string(void);
  */
 int hsd_ring_signature_degree(const int32_t* rowptr, const int32_t* col, int32_t n_nodes,
                               const int32_t* src_nodes, const int32_t* out_rows, int32_t n_src,
-                              int32_t hops, int32_t heavy_begin,
+                              int32_t hops,
                               const int32_t* bin_end, const float* delta, int32_t n_bins,
                               float* sig, int64_t sig_ld,
                               int32_t* ring_sizes, uint32_t* ring_bitmaps,
@@ -80,7 +82,7 @@ int hsd_ring_signature_degree(const int32_t* rowptr, const int32_t* col, int32_t
 /* Rings only (tools/hierarchy.py:25-38, model/HSD.py:87-94 ring sizes). */
 int hsd_bfs_rings(const int32_t* rowptr, const int32_t* col, int32_t n_nodes,
                   const int32_t* src_nodes, const int32_t* out_rows, int32_t n_src,
-                  int32_t hops, int32_t heavy_begin,
+                  int32_t hops,
                   int32_t* ring_sizes, uint32_t* ring_bitmaps, void* stream);
 
 /* ---- layout: row-major signatures -> K-major table for the pairwise kernel --

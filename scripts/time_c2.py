@@ -9,7 +9,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
 hops = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 g = powerlaw_graph(n, 5, seed=0)
 dg = engine.DeviceGraph.upload(g)
-print("n", n, "bins", dg.n_bins, "k_used", dg.k_used(hops), "heavy_begin", dg.heavy_begin)
+print("n", n, "bins", dg.n_bins, "k_used", dg.k_used(hops), "nnz", g.nnz)
 
 def ev():
     return torch.cuda.Event(enable_timing=True)

@@ -182,35 +182,14 @@ pairwise_l1_kernel(const __grid_constant__ CUtensorMap tmap, const PairArgs p) {
         // (ncu: stall_no_instruction 0.82 -> 0.09 per issue, profiles/r1_pairwise_notes.md).
 #pragma unroll UNROLL
         for (int kk = 0; kk < KC; ++kk) {
-#ifndef HSD_PAIR_VARIANT
-#define HSD_PAIR_VARIANT 2
-#endif
-#if HSD_PAIR_VARIANT == 3 || HSD_PAIR_VARIANT == 4
-            // 64-bit operand loads: register pairs instead of aligned quads give ptxas more freedom
-            const float2 a00 = *reinterpret_cast<const float2*>(&sm.a[s][kk][ty * 4]);
-            const float2 a01 = *reinterpret_cast<const float2*>(&sm.a[s][kk][ty * 4 + 2]);
-            const float2 a10 = *reinterpret_cast<const float2*>(&sm.a[s][kk][64 + ty * 4]);
-            const float2 a11 = *reinterpret_cast<const float2*>(&sm.a[s][kk][64 + ty * 4 + 2]);
-            const float2 b00 = *reinterpret_cast<const float2*>(&sm.b[s][kk][tx * 4]);
-            const float2 b01 = *reinterpret_cast<const float2*>(&sm.b[s][kk][tx * 4 + 2]);
-            const float2 b10 = *reinterpret_cast<const float2*>(&sm.b[s][kk][64 + tx * 4]);
-            const float2 b11 = *reinterpret_cast<const float2*>(&sm.b[s][kk][64 + tx * 4 + 2]);
-            const float av[8] = {a00.x, a00.y, a01.x, a01.y, a10.x, a10.y, a11.x, a11.y};
-            const float bv[8] = {b00.x, b00.y, b01.x, b01.y, b10.x, b10.y, b11.x, b11.y};
-#else
             const float4 a0 = *reinterpret_cast<const float4*>(&sm.a[s][kk][ty * 4]);
             const float4 a1 = *reinterpret_cast<const float4*>(&sm.a[s][kk][64 + ty * 4]);
             const float4 b0 = *reinterpret_cast<const float4*>(&sm.b[s][kk][tx * 4]);
             const float4 b1 = *reinterpret_cast<const float4*>(&sm.b[s][kk][64 + tx * 4]);
             const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
             const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#endif
-#if HSD_PAIR_VARIANT == 1 || HSD_PAIR_VARIANT == 4
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-#pragma unroll
-                for (int r = 0; r < 8; ++r) acc[r][q] += fabsf(av[r] - bv[q]);
-#elif HSD_PAIR_VARIANT == 2
+            // 64 subtracts, then 64 |.|-accumulates: issuing the subtracts as a block lets ptxas
+            // place d[][] and acc[][] in different register banks
             float d[8][8];
 #pragma unroll
             for (int r = 0; r < 8; ++r)
@@ -220,17 +199,10 @@ pairwise_l1_kernel(const __grid_constant__ CUtensorMap tmap, const PairArgs p) {
             for (int r = 0; r < 8; ++r)
 #pragma unroll
                 for (int q = 0; q < 8; ++q) acc[r][q] += fabsf(d[r][q]);
-#else
-#pragma unroll
-            for (int r = 0; r < 8; ++r)
-#pragma unroll
-                for (int q = 0; q < 8; ++q) acc[r][q] += fabsf(av[r] - bv[q]);
-#endif
         }
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(smem_u32(&sm.empty[s]));
     }
-
     // ===== epilogue: direct store (+ mirrored store for off-diagonal symmetric tiles) =====
     const int row_end = p.row0 + p.n_rows, col_end = p.col0 + p.n_cols;
     const bool full_tile = (i_base + TILE <= row_end) && (j_base + TILE <= col_end) && p.vec_ok;
@@ -314,8 +286,9 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 
 namespace hsd {
 
-static int launch_pairwise(const float* sigT, int32_t k_pad, int64_t n_pad, PairArgs a, long long n_tiles,
+static int launch_pairwise(const float* sigT, int32_t k_used, int64_t n_pad, PairArgs a, long long n_tiles,
                            cudaStream_t stream) {
+    const int32_t k_pad = (k_used + KC - 1) / KC * KC;
     auto encode = get_encode();
     if (!encode) {
         set_error("cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
@@ -358,12 +331,12 @@ static int launch_pairwise(const float* sigT, int32_t k_pad, int64_t n_pad, Pair
 
 }  // namespace hsd
 
-extern "C" int hsd_pairwise_l1(const float* sigT, int32_t k_pad, int64_t n_pad, int32_t row0,
+extern "C" int hsd_pairwise_l1(const float* sigT, int32_t k_used, int64_t n_pad, int32_t row0,
                                int32_t n_rows, int32_t col0, int32_t n_cols, int32_t symmetric,
                                float* out, int64_t ld_out, void* stream) {
     using namespace hsd;
     HSD_REQUIRE(sigT && out, "null pointer");
-    HSD_REQUIRE(k_pad > 0 && k_pad % KC == 0, "k_pad must be a positive multiple of HSD_PAIR_KCHUNK");
+    HSD_REQUIRE(k_used > 0, "k_used must be positive");
     HSD_REQUIRE(n_pad > 0 && n_pad % 4 == 0, "n_pad must be a multiple of 4");
     HSD_REQUIRE((reinterpret_cast<uintptr_t>(sigT) & 15) == 0, "sigT must be 16-byte aligned");
     HSD_REQUIRE(row0 >= 0 && col0 >= 0 && n_rows >= 0 && n_cols >= 0, "negative range");
@@ -382,15 +355,15 @@ extern "C" int hsd_pairwise_l1(const float* sigT, int32_t k_pad, int64_t n_pad, 
     a.shard_ptrs = nullptr; a.per = 1; a.tile_stride = 1; a.tile_offset = 0;
     const long long n_tiles = symmetric ? (long long)a.tiles_r * a.tiles_c - (long long)a.tiles_r * (a.tiles_r - 1) / 2
                                         : (long long)a.tiles_r * a.tiles_c;
-    return launch_pairwise(sigT, k_pad, n_pad, a, n_tiles, (cudaStream_t)stream);
+    return launch_pairwise(sigT, k_used, n_pad, a, n_tiles, (cudaStream_t)stream);
 }
 
-extern "C" int hsd_pairwise_l1_sharded(const float* sigT, int32_t k_pad, int64_t n_pad, int32_t n_nodes,
+extern "C" int hsd_pairwise_l1_sharded(const float* sigT, int32_t k_used, int64_t n_pad, int32_t n_nodes,
                                        int32_t rank, int32_t world, int32_t rows_per_rank,
                                        float* const* shard_ptrs, int64_t ld_out, void* stream) {
     using namespace hsd;
     HSD_REQUIRE(sigT && shard_ptrs, "null pointer");
-    HSD_REQUIRE(k_pad > 0 && k_pad % KC == 0, "k_pad must be a positive multiple of HSD_PAIR_KCHUNK");
+    HSD_REQUIRE(k_used > 0, "k_used must be positive");
     HSD_REQUIRE(n_pad > 0 && n_pad % 4 == 0 && n_nodes > 0 && n_nodes <= n_pad, "bad n_pad / n_nodes");
     HSD_REQUIRE((reinterpret_cast<uintptr_t>(sigT) & 15) == 0, "sigT must be 16-byte aligned");
     HSD_REQUIRE(world >= 1 && rank >= 0 && rank < world, "bad rank / world");
@@ -405,7 +378,7 @@ extern "C" int hsd_pairwise_l1_sharded(const float* sigT, int32_t k_pad, int64_t
     a.shard_ptrs = shard_ptrs; a.per = rows_per_rank; a.tile_stride = world; a.tile_offset = rank;
     const long long total = (long long)a.tiles_r * (a.tiles_r + 1) / 2;
     const long long mine = total > rank ? (total - rank + world - 1) / world : 0;
-    return launch_pairwise(sigT, k_pad, n_pad, a, mine, (cudaStream_t)stream);
+    return launch_pairwise(sigT, k_used, n_pad, a, mine, (cudaStream_t)stream);
 }
 
 extern "C" int hsd_fp32_peak_probe(float* sink, int32_t iters, int64_t* lane_ops_host, void* stream) {

@@ -154,8 +154,12 @@ def signature_transpose(sig: torch.Tensor, k_used: int, sigT: torch.Tensor, col0
 
 def pairwise_l1(sigT: torch.Tensor, n: int, row0: int = 0, n_rows: Optional[int] = None,
                 col0: int = 0, n_cols: Optional[int] = None, symmetric: Optional[bool] = None,
-                out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """out[i-row0, j-col0] = sum_k |sigT[k, i] - sigT[k, j]| (float32)."""
+                out: Optional[torch.Tensor] = None, k_used: Optional[int] = None) -> torch.Tensor:
+    """out[i-row0, j-col0] = sum_k |sigT[k, i] - sigT[k, j]| (float32).  k_used = number of
+    signature rows that hold data (default: all rows of the table)."""
+    k_used = sigT.shape[0] if k_used is None else k_used
+    if roundup(k_used, PAIR_KCHUNK) > sigT.shape[0]:
+        raise ValueError("signature table has fewer rows than k_used rounded up to the K chunk")
     n_rows = n - row0 if n_rows is None else n_rows
     n_cols = n - col0 if n_cols is None else n_cols
     if symmetric is None:
@@ -164,7 +168,7 @@ def pairwise_l1(sigT: torch.Tensor, n: int, row0: int = 0, n_rows: Optional[int]
         out = torch.empty((n_rows, n_cols), dtype=torch.float32, device=sigT.device)
     if out.shape[0] < n_rows or out.shape[1] < n_cols or out.stride(1) != 1:
         raise ValueError("out too small or not row-major")
-    check(lib.hsd_pairwise_l1(_ptr(sigT), sigT.shape[0], sigT.stride(0), row0, n_rows, col0, n_cols,
+    check(lib.hsd_pairwise_l1(_ptr(sigT), k_used, sigT.stride(0), row0, n_rows, col0, n_cols,
                               1 if symmetric else 0, out.data_ptr(), out.stride(0), _stream()))
     return out
 
@@ -192,7 +196,7 @@ def degree_distance_device(dg: DeviceGraph, hops: int, empty: str = "raise",
     signature_transpose(sig, k_used, sigT, 0)
     n_rows = n - row0 if n_rows is None else n_rows
     full = (row0 == 0 and n_rows == n)
-    D = pairwise_l1(sigT, n, row0, n_rows, 0, n, symmetric=full, out=out)
+    D = pairwise_l1(sigT, n, row0, n_rows, 0, n, symmetric=full, out=out, k_used=k_used)
     if check_status and empty == "raise" and int(status.item()) & 1:
         raise EmptyRingError("Distribution can't be empty.")
     return D, sizes
@@ -298,11 +302,11 @@ class HostDegreePipeline:
             if self.full:
                 # trapezoid: rows [p0, p0+pr) x cols [p0, N), mirrored into rows below
                 view = self.D[p0:, p0:]
-                check(lib.hsd_pairwise_l1(_ptr(self.sigT), self.sigT.shape[0], self.sigT.stride(0),
+                check(lib.hsd_pairwise_l1(_ptr(self.sigT), self.k_used, self.sigT.stride(0),
                                           p0, pr, p0, self.n - p0, 1, view.data_ptr(), self.D.stride(0), _stream()))
             else:
                 view = self.D[p0:]
-                check(lib.hsd_pairwise_l1(_ptr(self.sigT), self.sigT.shape[0], self.sigT.stride(0),
+                check(lib.hsd_pairwise_l1(_ptr(self.sigT), self.k_used, self.sigT.stride(0),
                                           self.row0 + p0, pr, 0, self.n, 0, view.data_ptr(), self.D.stride(0), _stream()))
             ev = torch.cuda.Event()
             ev.record(cur)

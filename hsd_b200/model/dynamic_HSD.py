@@ -109,7 +109,8 @@ class DynamicHSD(MultiHSD):
         if self._D is None or self._D.shape[0] != n or not self._pending:
             sigT = engine.alloc_signature_table(k_used, n, sig.device)
             engine.signature_transpose(sig, k_used, sigT, 0)
-            self._D = engine.pairwise_l1(sigT, n, symmetric=True, out=self._D if self._D is not None and self._D.shape[0] == n else None)
+            self._D = engine.pairwise_l1(sigT, n, symmetric=True, k_used=k_used,
+                                         out=self._D if self._D is not None and self._D.shape[0] == n else None)
             self.last_affected = torch.arange(n, device=sig.device)
             self._pending.clear()
             return self._D
@@ -119,14 +120,14 @@ class DynamicHSD(MultiHSD):
         if m * 2 >= n:   # rectangular |A| x N costs more than the symmetric full matrix
             sigT = engine.alloc_signature_table(k_used, n, sig.device)
             engine.signature_transpose(sig, k_used, sigT, 0)
-            engine.pairwise_l1(sigT, n, symmetric=True, out=self._D)
+            engine.pairwise_l1(sigT, n, symmetric=True, out=self._D, k_used=k_used)
         elif m > 0:
             # table = [all nodes | affected nodes]; rows = affected block, columns = all nodes
             n4 = engine.roundup(n, 4)
             sigT = engine.alloc_signature_table(k_used, n4 + m, sig.device)
             engine.signature_transpose(sig, k_used, sigT, 0)
             engine.signature_transpose(sig, k_used, sigT, n4, src_rows=aff.to(torch.int32).contiguous())
-            blk = engine.pairwise_l1(sigT, n4 + m, row0=n4, n_rows=m, col0=0, n_cols=n, symmetric=False)
+            blk = engine.pairwise_l1(sigT, n4 + m, row0=n4, n_rows=m, col0=0, n_cols=n, symmetric=False, k_used=k_used)
             self._D[aff, :] = blk
             self._D[:, aff] = blk.t()
         self._pending.clear()

@@ -122,15 +122,16 @@ class ShardedDegreeHSD:
             ev_before.record()
         if self.peer:
             from ._lib import check, lib
-            check(lib.hsd_pairwise_l1_sharded(engine._ptr(self.sigT), self.sigT.shape[0], self.sigT.stride(0),
+            check(lib.hsd_pairwise_l1_sharded(engine._ptr(self.sigT), self.k_used, self.sigT.stride(0),
                                               n, self.rank, self.world, self.per, engine._ptr(self.ptrs),
                                               self.ld_out, engine._stream()))
             return self.out[:self.n_rows]
         if self.n_rows == 0:
             return self.out[:0]
         if self.world == 1:
-            return engine.pairwise_l1(self.sigT, n, symmetric=True, out=self.out)
-        return engine.pairwise_l1(self.sigT, n, self.row0, self.n_rows, 0, n, symmetric=False, out=self.out)
+            return engine.pairwise_l1(self.sigT, n, symmetric=True, out=self.out, k_used=self.k_used)
+        return engine.pairwise_l1(self.sigT, n, self.row0, self.n_rows, 0, n, symmetric=False, out=self.out,
+                                  k_used=self.k_used)
 
     def peer_barrier(self) -> None:
         """A block is complete only when every rank's launch has stored its tiles into it."""

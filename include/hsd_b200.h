@@ -106,10 +106,11 @@ int hsd_signature_transpose(const float* sig, int64_t sig_ld, int32_t n_rows, in
  * reference fills dist_mat[i,j] = dist_mat[j,i] (model/HSD.py:112).  Panels of
  * rows processed in order therefore complete the matrix top to bottom, which is
  * what lets the host pipeline stream finished rows out while later panels compute.
- * sigT: float[k_pad][n_pad], k_pad % HSD_PAIR_KCHUNK == 0, n_pad % 4 == 0,
- * base 16-byte aligned; row0 % 4 == 0 and col0 % 4 == 0 (TMA tile origins must be
+ * sigT: float[k_pad][n_pad] with k_pad = k_used rounded up to HSD_PAIR_KCHUNK (rows
+ * k_used..k_pad-1 must be zero),
+ * n_pad % 4 == 0, base 16-byte aligned; row0 % 4 == 0 and col0 % 4 == 0 (TMA tile origins must be
  * 16-byte aligned). Tiles are staged by TMA (cp.async.bulk.tensor.2d). */
-int hsd_pairwise_l1(const float* sigT, int32_t k_pad, int64_t n_pad,
+int hsd_pairwise_l1(const float* sigT, int32_t k_used, int64_t n_pad,
                     int32_t row0, int32_t n_rows, int32_t col0, int32_t n_cols,
                     int32_t symmetric, float* out, int64_t ld_out, void* stream);
 
@@ -124,7 +125,7 @@ int hsd_pairwise_l1(const float* sigT, int32_t k_pad, int64_t n_pad,
  * G GPUs as on one.  Block r is complete once every rank's launch has finished
  * (the caller issues one barrier).  The reference mirrors dist_mat[i,j] = dist_mat[j,i]
  * the same way (model/HSD.py:112). */
-int hsd_pairwise_l1_sharded(const float* sigT, int32_t k_pad, int64_t n_pad, int32_t n_nodes,
+int hsd_pairwise_l1_sharded(const float* sigT, int32_t k_used, int64_t n_pad, int32_t n_nodes,
                             int32_t rank, int32_t world, int32_t rows_per_rank,
                             float* const* shard_ptrs, int64_t ld_out, void* stream);
 

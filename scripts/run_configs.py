@@ -37,7 +37,7 @@ if "c3" in which:
     k = dg.k_used(4)
     t_b, (sig, sizes, _, st) = timed(lambda: engine.ring_signature_degree(dg, 4))
     sigT = engine.alloc_signature_table(k, n, sig.device); engine.signature_transpose(sig, k, sigT)
-    t_p, _ = timed(lambda: engine.pairwise_l1(sigT, n, symmetric=True, out=out))
+    t_p, _ = timed(lambda: engine.pairwise_l1(sigT, n, symmetric=True, out=out, k_used=k))
     peak = engine.fp32_issue_peak()
     pairs = n * (n - 1) / 2
     print(json.dumps({"config": "C3 on 1 GPU", "n": n, "hops": 4, "K": k, "bfs_ms": t_b, "pairwise_ms": t_p,

@@ -25,7 +25,7 @@ for it in range(4):
     sigT = engine.alloc_signature_table(dg.k_used(hops), n, sig.device)
     engine.signature_transpose(sig, dg.k_used(hops), sigT)
     e[2].record()
-    engine.pairwise_l1(sigT, n, symmetric=True, out=out)
+    engine.pairwise_l1(sigT, n, symmetric=True, out=out, k_used=dg.k_used(hops))
     e[3].record()
     torch.cuda.synchronize()
     t = [e[i].elapsed_time(e[i + 1]) for i in range(3)]

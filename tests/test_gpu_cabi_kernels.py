@@ -22,7 +22,7 @@ def test_pairwise_l1_symmetric_exact(n, k):
     T = rng.integers(0, 50, size=(k, n)).astype(np.float32)
     sigT = engine.alloc_signature_table(k, n, "cuda")
     sigT[:k, :n] = torch.from_numpy(T).cuda()
-    D = engine.pairwise_l1(sigT, n, symmetric=True).cpu().numpy()
+    D = engine.pairwise_l1(sigT, n, symmetric=True, k_used=k).cpu().numpy()
     ref = _l1_ref(T.astype(np.float64), np.arange(n), np.arange(n))
     assert np.array_equal(D, ref)
 
@@ -52,7 +52,7 @@ def test_pairwise_l1_trapezoid_panels_compose_the_matrix():
     D = torch.full((n, n), -1.0, dtype=torch.float32, device="cuda")
     for p0, pr in [(0, 128), (128, 256), (384, 316)]:
         view = D[p0:, p0:]
-        check(lib.hsd_pairwise_l1(sigT.data_ptr(), sigT.shape[0], sigT.stride(0), p0, pr, p0, n - p0, 1,
+        check(lib.hsd_pairwise_l1(sigT.data_ptr(), k, sigT.stride(0), p0, pr, p0, n - p0, 1,
                                   view.data_ptr(), D.stride(0), torch.cuda.current_stream().cuda_stream))
     assert np.array_equal(D.cpu().numpy(), _l1_ref(T.astype(np.float64), np.arange(n), np.arange(n)))
 

@@ -27,7 +27,7 @@ def test_c_abi_argument_validation_without_gpu():
     assert rc == -1 and b"null" in lib.hsd_last_error_string()
     buf = (ctypes.c_float * 64)()
     p = ctypes.addressof(buf)
-    assert lib.hsd_pairwise_l1(p, 15, 128, 0, 1, 0, 1, 0, p, 128, None) == -1     # k_pad % 16
+    assert lib.hsd_pairwise_l1(p, 0, 128, 0, 1, 0, 1, 0, p, 128, None) == -1      # k_used > 0
     assert lib.hsd_pairwise_l1(p, 16, 130, 0, 1, 0, 1, 0, p, 130, None) == -1     # n_pad % 4
     assert lib.hsd_pairwise_l1(p, 16, 128, 0, 64, 0, 32, 1, p, 128, None) == -1   # symmetric trapezoid
     assert lib.hsd_pairwise_l1(p, 16, 128, 2, 64, 0, 32, 0, p, 128, None) == -1   # TMA origin alignment

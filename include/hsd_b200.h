@@ -188,6 +188,8 @@ int hsd_pairwise_worker(const double* sorted_vals, const int32_t* order,
  * with L = D - A taken from the CSR (original node order, unit weights), then
  * the reference threshold x > thr ? x : 0 (model/HSD.py:65).
  *   coeff_host  HOST double[n_scales][order+1] (copied into the launch arguments)
+ *   n_cols   even (columns are processed in 16-byte pairs); col0 + n_cols may exceed n_nodes by one
+ *            (an all-zero impulse column) so an odd node count can be padded
  *   work     double[3][n_nodes][n_cols]   (T ring buffer)
  *   out      double[n_scales][n_nodes][n_cols]; out[s][v][c] = Psi_s[col0+c][v] (= Psi_s[v][col0+c], symmetric)
  */

@@ -1,0 +1,94 @@
+"""BASELINE.json's headline size (C2: BA 20 000 nodes, 3 hops, full N x N) through properties
+that do not need the oracle to finish 2e8 pairs: symmetry, zero diagonal, the triangle
+inequality (a sum of W1 metrics is a metric), agreement of the three product paths
+(device, host pipeline, emulated sharding), a row-sum checksum, and a sampled comparison
+against the oracle (scipy W1 over the reference's BFS rings)."""
+import numpy as np
+import pytest
+
+from oracle import hsd_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def c2():
+    import torch
+    from hsd_b200 import engine
+    from hsd_b200.graph import powerlaw_graph
+    g = powerlaw_graph(20000, 5, seed=0)
+    dg = engine.DeviceGraph.upload(g)
+    D, sizes = engine.degree_distance_device(dg, 3)
+    torch.cuda.synchronize()
+    return g, dg, D, sizes
+
+
+def test_c2_structure(c2):
+    import torch
+    g, dg, D, sizes = c2
+    n = g.n
+    assert D.shape == (n, n) and D.dtype == torch.float32
+    assert torch.equal(D, D.t())
+    assert torch.all(torch.diagonal(D) == 0)
+    assert torch.all(D >= 0) and torch.isfinite(D).all()
+    # ring sizes: hop 0 is the node, hop 1 its degree
+    assert torch.all(sizes[:, 0] == 1)
+    assert np.array_equal(sizes[:, 1].cpu().numpy(), g.degree)
+    assert dg.n_bins == 146 and dg.k_used(3) == 436           # B = 146 at C2
+
+
+def test_c2_triangle_inequality_sampled(c2):
+    import torch
+    g, dg, D, _ = c2
+    rng = np.random.default_rng(0)
+    idx = torch.from_numpy(rng.integers(0, g.n, size=(200000, 3))).cuda()
+    a, b, c = idx[:, 0], idx[:, 1], idx[:, 2]
+    lhs = D[a, c]
+    rhs = D[a, b] + D[b, c]
+    assert torch.all(lhs <= rhs * (1 + 1e-5) + 1e-4)
+
+
+def test_c2_sampled_pairs_match_oracle(c2):
+    g, dg, D, sizes = c2
+    rng = np.random.default_rng(1)
+    rows = [0, 7, 19999]                       # a hub, an early node, the last node
+    cols = sorted(set(rng.integers(0, g.n, size=150).tolist()) | {1, 2, 3})
+    adj = [g.neighbors(i).astype(np.int64) for i in range(g.n)]
+    ref = O.degree_distance_rows(adj, 3, rows, cols)
+    got = D[rows][:, cols].cpu().numpy().astype(np.float64)
+    np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-6 * ref.max())
+    rings = O.all_rings(adj, 3, rows)
+    for r in rows:
+        assert sizes[r].tolist() == [len(l) for l in rings[r]]
+
+
+def test_c2_paths_agree_bitwise(c2):
+    import torch
+    from hsd_b200 import engine
+    from hsd_b200.sharded import ShardedDegreeHSD, shard_rows
+    g, dg, D, _ = c2
+    n = g.n
+    checksum = D.double().sum(1)
+    # host pipeline (pinned host buffers, panel-streamed D2H)
+    pipe = engine.HostDegreePipeline(g, 3)
+    out = torch.empty((n, n), dtype=torch.float32).pin_memory()
+    pipe.run(out)
+    assert torch.equal(out.cuda().double().sum(1), checksum)
+    assert torch.equal(out[12345].cuda(), D[12345])
+    del out
+    # 8 emulated ranks with peer-memory mirroring
+    world = 8
+    per = shard_rows(n, world, 0)[2]
+    blocks = [torch.zeros((per, engine.roundup(n, 4)), dtype=torch.float32, device="cuda") for _ in range(world)]
+    plans = [ShardedDegreeHSD(dg, 3, r, world, peer=True, peer_blocks=blocks) for r in range(world)]
+    for p in plans:
+        p.signatures()
+    for p in plans:
+        for q in plans:
+            sl = slice(q.rank * q.per, q.rank * q.per + q.n_src)
+            p.sig_all[sl] = q.sig_all[sl]
+    for p in plans:
+        p.distances()
+    torch.cuda.synchronize()
+    got = torch.cat([b[:, :n] for b in blocks], 0)[:n]
+    assert torch.equal(got, D)

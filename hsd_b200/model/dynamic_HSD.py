@@ -9,8 +9,12 @@ recompute on the updated graph.
 Affected set (degree signal): a node's k-hop rings change only if it lies within
 hop-1 of an endpoint of a new edge, and the degree of a ring member changes only
 for the endpoints themselves, so every changed signature belongs to a node within
-``hop`` hops (in the new graph) of an endpoint.  That ball is the OR of the ring
-bitmaps the BFS kernel produces for the endpoints.
+``hop`` hops (in the new graph) of an endpoint (``affected_nodes_device``: the OR of
+the BFS kernel's ring bitmaps for the endpoints).  The update itself uses the exact
+set instead: all signatures are rebuilt (the BFS kernel costs ~1 % of the pairwise
+kernel) and compared bit for bit with the previous table; only rows whose signature
+differs are recomputed.  When the set of distinct degrees (the shared support)
+changes, every signature changes representation and the update is a full recompute.
 """
 from __future__ import annotations
 
@@ -34,6 +38,8 @@ class DynamicHSD(MultiHSD):
         self.embeddings = {}
         self._D = None           # device-resident distance matrix kept across updates
         self._pending = set()    # endpoints (node labels) of edges inserted since the last update
+        self._sig_prev = None    # signature table / support of the matrix in self._D
+        self._support_prev = None
         self.last_affected = None
 
     def init(self):
@@ -106,7 +112,11 @@ class DynamicHSD(MultiHSD):
         sig, _, _, status = engine.ring_signature_degree(dg, hops, empty=self.empty)
         if self.empty == "raise" and int(status.item()) & 1:
             raise engine.EmptyRingError("Distribution can't be empty.")
-        if self._D is None or self._D.shape[0] != n or not self._pending:
+        prev, prev_support = self._sig_prev, self._support_prev
+        self._sig_prev, self._support_prev = sig, dg.support
+        same_layout = (self._D is not None and self._D.shape[0] == n and prev is not None
+                       and prev.shape == sig.shape and np.array_equal(prev_support, dg.support))
+        if not same_layout:
             sigT = engine.alloc_signature_table(k_used, n, sig.device)
             engine.signature_transpose(sig, k_used, sigT, 0)
             self._D = engine.pairwise_l1(sigT, n, symmetric=True, k_used=k_used,
@@ -114,7 +124,7 @@ class DynamicHSD(MultiHSD):
             self.last_affected = torch.arange(n, device=sig.device)
             self._pending.clear()
             return self._D
-        aff = self.affected_nodes_device()
+        aff = torch.nonzero((sig != prev).any(dim=1), as_tuple=False).reshape(-1)   # exact changed set
         self.last_affected = aff
         m = int(aff.numel())
         if m * 2 >= n:   # rectangular |A| x N costs more than the symmetric full matrix

@@ -42,6 +42,11 @@ def test_incremental_equals_from_scratch(n, k, hop):
     mask[aff] = True
     assert not changed[~mask][:, ~mask].any()
     assert 0 < len(aff) <= n
+    # the exact changed set is inside the analytic bound: nodes within `hop` hops of an endpoint
+    m._pending.update(x for e in new_edges for x in e)
+    ball = set(m.affected_nodes_device().cpu().numpy().tolist())
+    m._pending.clear()
+    assert set(aff.tolist()) <= ball
 
 
 def test_add_node_grows_matrix():

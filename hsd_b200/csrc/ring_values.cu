@@ -123,6 +123,47 @@ struct PaddedAsc {
     }
 };
 
+// The three metrics of tools/metrics.py::calculate_distance that the HSD path reaches, on two
+// zero-padded ascending sequences of equal length L.  MakeP / MakeQ build a fresh stream (the
+// Gaussian metric needs two passes).
+//   0 'wasserstein'        scipy on equal-length samples == mean |p_(k) - q_(k)|   (:186-190)
+//   1 'hellinger'          sqrt(max(1 - sum sqrt(p q), 0)) with 1e-6 snapping        (:117-138)
+//   2 'wasserstein_guass'  (u1-u2)^2 + s1 + s2 - 2 sqrt(s1 s2), s = population var   (:54-71)
+template <typename MakeP, typename MakeQ>
+__device__ __forceinline__ double aligned_metric(int metric, int L, MakeP make_p, MakeQ make_q) {
+    auto P = make_p();
+    auto Q = make_q();
+    if (metric == 0) {
+        double s = 0.0;
+        for (int k = 0; k < L; ++k) s += fabs(P.next() - Q.next());
+        return s / (double)L;
+    }
+    if (metric == 1) {
+        double bc = 0.0;
+        for (int k = 0; k < L; ++k) {
+            const double px = P.next(), qx = Q.next();
+            if (px < 0.0 || qx < 0.0) continue;
+            bc += sqrt(fmax(px * qx, 0.0));
+        }
+        if (fabs(bc) <= 1e-6) bc = 0.0;
+        else if (fabs(bc - 1.0) <= fmax(1e-9 * fmax(fabs(bc), 1.0), 1e-6)) bc = 1.0;
+        return sqrt(fmax(1.0 - bc, 0.0));
+    }
+    double sp = 0.0, sq = 0.0;
+    for (int k = 0; k < L; ++k) { sp += P.next(); sq += Q.next(); }
+    const double u1 = sp / (double)L, u2 = sq / (double)L;
+    auto P2 = make_p();
+    auto Q2 = make_q();
+    double vp = 0.0, vq = 0.0;
+    for (int k = 0; k < L; ++k) {
+        const double a = P2.next() - u1, b = Q2.next() - u2;
+        vp += a * a;
+        vq += b * b;
+    }
+    const double s1 = vp / (double)L, s2 = vq / (double)L;
+    return (u1 - u2) * (u1 - u2) + s1 + s2 - 2.0 * sqrt(s1 * s2);
+}
+
 __global__ void __launch_bounds__(256)
 pairwise_aligned_kernel(const double* __restrict__ vals, const int64_t* __restrict__ offsets,
                         const int32_t* __restrict__ sizes, int n_total, int hops1, int hop_begin,
@@ -138,23 +179,9 @@ pairwise_aligned_kernel(const double* __restrict__ vals, const int64_t* __restri
         const int ni = sizes[si], nj = sizes[sj];
         const int L = max(ni, nj);
         if (L == 0) continue;  // tools/metrics.py:170-171
-        PaddedAsc P(vals + offsets[si], ni, L), Q(vals + offsets[sj], nj, L);
-        if (metric == 0) {
-            // scipy on equal-length samples == mean |p_(k) - q_(k)|
-            double s = 0.0;
-            for (int k = 0; k < L; ++k) s += fabs(P.next() - Q.next());
-            d += s / (double)L;
-        } else {
-            double bc = 0.0;  // tools/metrics.py:117-138
-            for (int k = 0; k < L; ++k) {
-                const double px = P.next(), qx = Q.next();
-                if (px < 0.0 || qx < 0.0) continue;
-                bc += sqrt(fmax(px * qx, 0.0));
-            }
-            if (fabs(bc) <= 1e-6) bc = 0.0;
-            else if (fabs(bc - 1.0) <= fmax(1e-9 * fmax(fabs(bc), 1.0), 1e-6)) bc = 1.0;
-            d += sqrt(fmax(1.0 - bc, 0.0));
-        }
+        const double* pi = vals + offsets[si];
+        const double* pj = vals + offsets[sj];
+        d += aligned_metric(metric, L, [&] { return PaddedAsc(pi, ni, L); }, [&] { return PaddedAsc(pj, nj, L); });
     }
     out[(int64_t)i * ld + j] = d;
     out[(int64_t)j * ld + i] = d;
@@ -206,23 +233,10 @@ pairwise_worker_kernel(const double* __restrict__ sorted_vals, const int32_t* __
         const int ni = sizes[i * hops1 + h], nj = sizes[j * hops1 + h];
         const int L = max(ni, nj);
         if (L == 0) continue;
-        RingStream P(sv, ord, bit_of, bitmaps + ((int64_t)i * hops1 + h) * n_words, n, ni, L);
-        RingStream Q(sv, ord, bit_of, bitmaps + ((int64_t)j * hops1 + h) * n_words, n, nj, L);
-        if (metric == 0) {
-            double s = 0.0;
-            for (int k = 0; k < L; ++k) s += fabs(P.next() - Q.next());
-            d += s / (double)L;
-        } else {
-            double bc = 0.0;
-            for (int k = 0; k < L; ++k) {
-                const double px = P.next(), qx = Q.next();
-                if (px < 0.0 || qx < 0.0) continue;
-                bc += sqrt(fmax(px * qx, 0.0));
-            }
-            if (fabs(bc) <= 1e-6) bc = 0.0;
-            else if (fabs(bc - 1.0) <= fmax(1e-9 * fmax(fabs(bc), 1.0), 1e-6)) bc = 1.0;
-            d += sqrt(fmax(1.0 - bc, 0.0));
-        }
+        const uint32_t* bi = bitmaps + ((int64_t)i * hops1 + h) * n_words;
+        const uint32_t* bj = bitmaps + ((int64_t)j * hops1 + h) * n_words;
+        d += aligned_metric(metric, L, [&] { return RingStream(sv, ord, bit_of, bi, n, ni, L); },
+                            [&] { return RingStream(sv, ord, bit_of, bj, n, nj, L); });
     }
     out[(int64_t)i * ld + j] = d;
 }
@@ -279,7 +293,7 @@ extern "C" int hsd_pairwise_aligned(const double* vals, const int64_t* offsets,
                                     int32_t n_rows, double* out, int64_t ld_out, void* stream) {
     using namespace hsd;
     HSD_REQUIRE(vals && offsets && ring_sizes && out, "null pointer");
-    HSD_REQUIRE(metric == 0 || metric == 1, "metric must be 0 (wasserstein) or 1 (hellinger)");
+    HSD_REQUIRE(metric >= 0 && metric <= 2, "metric must be 0 (wasserstein), 1 (hellinger) or 2 (wasserstein_guass)");
     HSD_REQUIRE(n_total > 0 && hops >= 0 && 0 <= hop_begin && hop_begin <= hop_end && hop_end <= hops + 1,
                 "bad hop range");
     HSD_REQUIRE(row0 >= 0 && n_rows >= 0 && row0 + n_rows <= n_total && ld_out >= n_total, "bad row range");
@@ -299,7 +313,7 @@ extern "C" int hsd_pairwise_worker(const double* sorted_vals, const int32_t* ord
                                    double* out, int64_t ld_out, void* stream) {
     using namespace hsd;
     HSD_REQUIRE(sorted_vals && order && ring_bitmaps && ring_sizes && out, "null pointer");
-    HSD_REQUIRE(metric == 0 || metric == 1, "metric must be 0 (wasserstein) or 1 (hellinger)");
+    HSD_REQUIRE(metric >= 0 && metric <= 2, "metric must be 0 (wasserstein), 1 (hellinger) or 2 (wasserstein_guass)");
     HSD_REQUIRE(n_nodes > 0 && hops >= 0 && hop_end >= 0 && hop_end <= hops + 1, "bad hop range");
     HSD_REQUIRE(row0 >= 0 && n_rows >= 0 && row0 + n_rows <= n_nodes && ld_out >= n_nodes, "bad row range");
     if (n_rows == 0) return HSD_OK;

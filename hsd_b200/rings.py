@@ -18,6 +18,12 @@ from . import engine
 from .graph import CSRGraph
 
 
+# metrics of tools/metrics.py::calculate_distance available on the GPU (the other names the
+# reference lists — l1, l2, kl, symmetric_kl, js — raise ValueError there on un-normalised ring
+# signals, tools/metrics.py:39-51, and are not part of the HSD path)
+METRIC_IDS = {"wasserstein": 0, "hellinger": 1, "wasserstein_guass": 2}
+
+
 @dataclass
 class RingSet:
     bitmaps: torch.Tensor            # int32[N, H+1, words]; row = source's original index
@@ -122,7 +128,7 @@ def value_distance(psi: torch.Tensor, rings: RingSet, hop_begin: int = 0,
         if int(status.item()) & 1:
             raise engine.EmptyRingError("Distribution can't be empty.")
     elif mode == "aligned":
-        m = {"wasserstein": 0, "hellinger": 1}.get(metric.lower())
+        m = METRIC_IDS.get(str(metric).lower())
         if m is None:
             raise NotImplementedError("{} metric is not implemented.".format(metric))
         for r0 in range(0, n, 32768):
@@ -139,7 +145,7 @@ def worker_distance(psi: torch.Tensor, rings: RingSet, hop_end: int, metric: str
     D[i, j] = D[j, i] = sum_{h < hop_end} aligned(Psi[i, ring_h(i)], Psi[i, ring_h(j)]), i < j."""
     from ._lib import check, lib
     n, hops = rings.n, rings.hops
-    m = {"wasserstein": 0, "hellinger": 1}.get(str(metric).lower())
+    m = METRIC_IDS.get(str(metric).lower())
     if m is None:
         if not metric or not isinstance(metric, str):
             raise TypeError("Need to specify a metric.")

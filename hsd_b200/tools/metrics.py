@@ -42,4 +42,8 @@ def calculate_distance(p, q, metric):
         return float(np.mean(np.abs(p - q)))
     if metric == 'hellinger':
         return hellinger_distance(p, q)
+    if metric == 'wasserstein_guass':
+        u1, u2 = np.mean(p), np.mean(q)
+        s1, s2 = np.mean(np.square(p - u1)), np.mean(np.square(q - u2))
+        return float((u1 - u2) ** 2 + s1 + s2 - 2 * (s1 * s2) ** 0.5)
     raise NotImplementedError("{} is outside the HSD hot path; use the reference's tools/metrics.py".format(metric))

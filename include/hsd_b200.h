@@ -159,7 +159,8 @@ int hsd_pairwise_w1_merge(const double* vals, const int64_t* offsets, const int3
  * sorts, and calls scipy on equal-length arrays, i.e.
  *   d = (1/L) * sum_k |p_desc[k] - q_desc[k]|,  L = max(n_p, n_q), 0 when both empty.
  * Same ragged ascending `vals` as above. metric: 0 = 'wasserstein', 1 = 'hellinger'
- * (tools/metrics.py:117-138 on the same aligned ascending arrays). */
+ * (tools/metrics.py:117-138 on the same aligned ascending arrays), 2 = 'wasserstein_guass'
+ * (tools/metrics.py:54-71: (u1-u2)^2 + s1 + s2 - 2 sqrt(s1 s2) of the padded arrays). */
 int hsd_pairwise_aligned(const double* vals, const int64_t* offsets, const int32_t* ring_sizes,
                          int32_t n_total, int32_t hops, int32_t hop_begin, int32_t hop_end,
                          int32_t metric, int32_t row0, int32_t n_rows,

@@ -129,7 +129,7 @@ def aligned_distance(p: Sequence[float], q: Sequence[float], metric: str = "wass
     if not metric or not isinstance(metric, str):
         raise TypeError("Need to specify a metric.")
     metric = metric.lower()
-    if metric not in ("wasserstein", "hellinger"):
+    if metric not in ("wasserstein", "hellinger", "wasserstein_guass"):
         raise NotImplementedError("{} metric is not implemented.".format(metric))
     length = max(len(p), len(q))
     p = np.sort(np.asarray(list(p) + [0.0] * (length - len(p)), dtype=np.float64))
@@ -138,6 +138,10 @@ def aligned_distance(p: Sequence[float], q: Sequence[float], metric: str = "wass
         return 0.0
     if metric == "wasserstein":
         return w1(p, q)
+    if metric == "wasserstein_guass":   # tools/metrics.py:54-71
+        u1, u2 = np.mean(p), np.mean(q)
+        s1, s2 = np.mean(np.square(p - u1)), np.mean(np.square(q - u2))
+        return float((u1 - u2) ** 2 + s1 + s2 - 2 * (s1 * s2) ** 0.5)
     bc = 0.0
     for px, qx in zip(p, q):
         if px < 0 or qx < 0:

@@ -134,7 +134,7 @@ def main():
         if name == "karate":
             # model/HSD.py:140-161 as written (needs self.wavelets, F7)
             m.wavelets = W
-            for metric in ["wasserstein", "hellinger"]:
+            for metric in ["wasserstein", "hellinger", "wasserstein_guass"]:
                 m.metric = metric
                 rows_ = np.stack([m._calculate_worker(i) for i in range(m.n_node)])
                 out[f"karate_worker_{metric}"] = rows_
@@ -172,7 +172,7 @@ def main():
     P = [list(rng.random(int(n))) for n in rng.integers(0, 9, size=24)]
     out["aligned_cases_len"] = np.array([len(p) for p in P], dtype=np.int32)
     out["aligned_cases_flat"] = np.array([x for p in P for x in p])
-    for metric in ["wasserstein", "hellinger"]:
+    for metric in ["wasserstein", "hellinger", "wasserstein_guass"]:
         out[f"aligned_{metric}"] = np.array([[metrics.calculate_distance(list(p), list(q), metric)
                                               for q in P] for p in P])
     np.savez_compressed(os.path.join(OUT, "reference_runs.npz"), **out)

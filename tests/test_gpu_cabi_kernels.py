@@ -130,11 +130,14 @@ def test_value_mode_kernels_on_ragged_signals():
     empties = any(len(ref_rings[i][h]) == 0 for i in range(n) for h in range(3))
     Da = rings.value_distance(psi_d, rs, mode="aligned", metric="wasserstein").cpu().numpy()
     Dh = rings.value_distance(psi_d, rs, mode="aligned", metric="hellinger").cpu().numpy()
+    Dg = rings.value_distance(psi_d, rs, mode="aligned", metric="wasserstein_guass").cpu().numpy()
     for i, j in [(0, 1), (5, 40), (22, 59)]:
         wa = sum(O.aligned_distance(list(psi[i, ref_rings[i][h]]), list(psi[j, ref_rings[j][h]]), "wasserstein") for h in range(3))
         wh = sum(O.aligned_distance(list(psi[i, ref_rings[i][h]]), list(psi[j, ref_rings[j][h]]), "hellinger") for h in range(3))
         assert Da[i, j] == pytest.approx(wa, rel=1e-12, abs=1e-14) and Da[j, i] == Da[i, j]
         assert Dh[i, j] == pytest.approx(wh, rel=1e-12, abs=1e-14)
+        wg = sum(O.aligned_distance(list(psi[i, ref_rings[i][h]]), list(psi[j, ref_rings[j][h]]), "wasserstein_guass") for h in range(3))
+        assert Dg[i, j] == pytest.approx(wg, rel=1e-10, abs=1e-12)
     if empties:
         with pytest.raises(ValueError):
             rings.value_distance(psi_d, rs, mode="w1")

@@ -80,7 +80,7 @@ def test_hierarchical_degree_and_coefficients(golden_graphs, golden_runs):
             assert sorted(coeffs[v][h]) == sorted(ref[i][h])
 
 
-@pytest.mark.parametrize("metric", ["wasserstein", "hellinger"])
+@pytest.mark.parametrize("metric", ["wasserstein", "hellinger", "wasserstein_guass"])
 def test_parallel_calculate_HSD_matches_reference_worker(golden_graphs, golden_runs, metric):
     """model/HSD.py:118-161 as written (hops 0..hop-1, both signals from row startIndex)."""
     from model import HSD

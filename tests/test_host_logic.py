@@ -33,7 +33,7 @@ def test_c_abi_argument_validation_without_gpu():
     assert lib.hsd_pairwise_l1(p, 16, 128, 2, 64, 0, 32, 0, p, 128, None) == -1   # TMA origin alignment
     assert lib.hsd_ring_signature_degree(None, None, 4, None, None, 1, 2, None, None, 1, None, 0,
                                          None, None, 0, None, None) == -1
-    assert lib.hsd_pairwise_aligned(p, p, p, 4, 2, 0, 3, 7, 0, 1, p, 4, None) == -1  # metric
+    assert lib.hsd_pairwise_aligned(p, p, p, 4, 2, 0, 3, 7, 0, 1, p, 4, None) == -1  # metric id
     assert lib.hsd_ring_reduce(p, 1, 4, 4, p, p, None, 9, 0, p, None) == -1          # hops > 7
     with pytest.raises(HSDError):
         check(lib.hsd_cheb_spmm(p, p, 4, -1.0, p, 1, 3, 0, 4, 0.0, p, p, None))
@@ -155,3 +155,22 @@ def test_product_package_never_touches_the_oracle_or_reference():
     assert not bad, bad
     for path in [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")]:
         assert "/root/reference" not in open(path).read()
+
+
+def test_rw_formats_round_trip(tmp_path, robust_csv):
+    """tools/rw.py formats: the CSV layout of the reference's golden robust.csv and the
+    distance edge list."""
+    from tools import rw, save_vectors_dict
+    vecs = {int(n): list(v[:12]) for n, v in zip(robust_csv["node"], robust_csv["values"])}
+    p = tmp_path / "v.csv"
+    save_vectors_dict(vecs, str(p))
+    first = open(p).readline().strip().split(",")
+    assert first[0] == str(int(robust_csv["node"][0])) and first[1] == "%.8f" % robust_csv["values"][0][0]
+    back = rw.read_vectors(str(p))
+    assert np.allclose(back[str(int(robust_csv["node"][3]))], robust_csv["values"][3][:12], atol=1e-8)
+    D = np.array([[0, 1.5, 2.0], [1.5, 0, 0.25], [2.0, 0.25, 0]])
+    q = tmp_path / "d.edgelist"
+    rw.save_distance_edgelist(str(q), [0, 1, 2], D)
+    assert np.array_equal(rw.read_distance(str(q), 3), D)
+    with pytest.raises(FileNotFoundError):
+        rw.read_vectors(str(tmp_path / "missing.csv"))

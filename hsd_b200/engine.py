@@ -202,6 +202,22 @@ def degree_distance_device(dg: DeviceGraph, hops: int, empty: str = "raise",
     return D, sizes
 
 
+def topk_rows(D: torch.Tensor, k: int, self_col0: int = 0, n_cols: Optional[int] = None,
+              col_mask: Optional[torch.Tensor] = None):
+    """k nearest neighbours of every row of a float32 distance block (row r is node self_col0 + r).
+    Returns (idx int32[n_rows, k], dist float32[n_rows, k]) ordered by (distance, column).
+    col_mask: optional int32 bitmap over columns (bit j set = column j may be a neighbour)."""
+    if D.dtype != torch.float32 or D.stride(1) != 1:
+        raise ValueError("D must be a row-major float32 CUDA tensor")
+    n_rows = D.shape[0]
+    n_cols = D.shape[1] if n_cols is None else n_cols
+    idx = torch.empty((n_rows, k), dtype=torch.int32, device=D.device)
+    val = torch.empty((n_rows, k), dtype=torch.float32, device=D.device)
+    check(lib.hsd_topk_rows(D.data_ptr(), D.stride(0), n_rows, n_cols, k, self_col0, _ptr(col_mask),
+                            _ptr(idx), _ptr(val), _stream()))
+    return idx, val
+
+
 def fp32_issue_peak(iters: int = 20000, reps: int = 3) -> float:
     """Measured FP32 CUDA-core issue rate in lane-ops/s (FADD sub + |.|-accumulate mix)."""
     dev = require_cuda()

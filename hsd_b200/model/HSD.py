@@ -216,6 +216,16 @@ class HSD(object):
             return out
         return D.cpu().numpy().astype(np.float64, copy=False)
 
+    def nearest_neighbors(self, k, scale=None, approx=False):
+        """(idx, dist): the k structurally closest nodes of every node, selected on the device
+        from the resident distance matrix — what a precomputed-metric KNN (tools/evaluate.py:61-69)
+        needs, without moving the N x N matrix to the host.  idx are node indices (model.nodes)."""
+        D = self.structural_distance_device(scale, approx)
+        if D.dtype != torch.float32:
+            D = D.to(torch.float32)
+        idx, val = engine.topk_rows(D.contiguous(), k)
+        return idx.cpu().numpy(), val.cpu().numpy()
+
     def parallel_calculate_HSD(self, n_workers=3, row_signal="reference"):
         """model/HSD.py:118-137 with the worker of :140-161: hops 0..hop-1 of the zero-padded
         'aligned' distance (tools/metrics.py:151-192).  row_signal="reference" reproduces the

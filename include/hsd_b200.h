@@ -220,6 +220,18 @@ int hsd_ring_reduce(const double* psiT, int32_t n_scales, int32_t n_nodes, int32
 int hsd_characteristic_function(const double* psi, int64_t psi_ld, int32_t n_rows, int32_t n_cols,
                                 const double* sample_points, int32_t n_points, double* out, void* stream);
 
+/* ---- K7: k nearest neighbours per row of the distance matrix -------------------
+ * The consumer right after the path: the reference passes the N x N ndarray to sklearn's
+ * precomputed-metric KNN (tools/evaluate.py:61-69, called from main.py:29).  Here the
+ * selection runs on the device-resident (possibly row-sharded) matrix: for row r the k
+ * smallest D[r][j], j != self_col0 + r, j allowed by col_mask (nullable bitmap over columns;
+ * lets a caller restrict neighbours to a training fold), ordered by (distance, column).
+ *   idx_out int32[n_rows][k] (-1 where fewer than k candidates), val_out float[n_rows][k]; 1 <= k <= 64.
+ * Distances must be >= 0 (radix select on the bit pattern). */
+int hsd_topk_rows(const float* D, int64_t ld, int32_t n_rows, int32_t n_cols, int32_t k,
+                  int32_t self_col0, const uint32_t* col_mask, int32_t* idx_out, float* val_out,
+                  void* stream);
+
 /* ---- measurement helper: FP32 CUDA-core issue peak ---------------------------
  * Runs a register-only FADD kernel (same sub + |.|-accumulate instruction mix as
  * the pairwise inner loop, no memory) and returns lane-ops in *lane_ops; the

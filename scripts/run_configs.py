@@ -85,3 +85,33 @@ if "c5" in which:
         t0 = time.perf_counter(); D = m.structural_distance_update(); torch.cuda.synchronize(); t_inc = time.perf_counter() - t0
         print(json.dumps({"config": "C5", "n": n, "hop": hop, "inserted_edges": k_ins, "affected_rows": int(m.last_affected.numel()),
                           "full_s": t_full, "incremental_s": t_inc}))
+
+if "c4full" in which:
+    n, order, S, hop = 50000, 30, 4, 3
+    G = nx.barabasi_albert_graph(n, 5, seed=0)
+    from model import MultiHSD
+    t0 = time.perf_counter(); m = MultiHSD(G, "ba50k", hop, S); t_init = time.perf_counter() - t0
+    m.scales = np.exp(np.linspace(np.log(0.01), np.log(40.0 / m.lmax), S)); m.CHEB_ORDER = order
+    m._rings(); torch.cuda.synchronize()
+    t0 = time.perf_counter(); emb = m.embed_device(); torch.cuda.synchronize(); t = time.perf_counter() - t0
+    byts = order * (8.0 * m.csr.nnz + 4 * (n + 1) + (3 + 2 * S) * 8.0 * n * n)
+    print(json.dumps({"config": "C4 full: MultiHSD.embed_device", "n": n, "hop": hop, "order": order, "scales": S,
+                      "init_s": t_init, "embed_s": t, "alg_GBs_incl_ring_reduce": byts / t / 1e9, "hbm_peak": peaks["hbm_gbs"],
+                      "checksum": float(emb.sum()), "emb_shape": list(emb.shape)}))
+
+if "c5h2" in which:
+    n, hop = 100000, 2
+    G = nx.barabasi_albert_graph(n, 5, seed=0)
+    from model import DynamicHSD
+    m = DynamicHSD(G, "ba100k", hop, 1, "wasserstein", signal="degree")
+    t0 = time.perf_counter(); m.structural_distance_update(); torch.cuda.synchronize(); t_full = time.perf_counter() - t0
+    rng = np.random.default_rng(1)
+    for k_ins in [5, 50]:
+        edges = set()
+        while len(edges) < k_ins:
+            u, v = (int(x) for x in rng.integers(0, n, 2))
+            if u != v and not m.graph.has_edge(u, v): edges.add((min(u, v), max(u, v)))
+        m.dynamic_add_edges(sorted(edges))
+        t0 = time.perf_counter(); D = m.structural_distance_update(); torch.cuda.synchronize(); t_inc = time.perf_counter() - t0
+        print(json.dumps({"config": "C5 variant hop=2", "n": n, "hop": hop, "inserted_edges": k_ins,
+                          "affected_rows": int(m.last_affected.numel()), "full_s": t_full, "incremental_s": t_inc}))

@@ -146,3 +146,46 @@ def test_value_mode_kernels_on_ragged_signals():
         for i, j in [(0, 1), (5, 40), (22, 59)]:
             ww = sum(O.w1(psi[i, ref_rings[i][h]], psi[j, ref_rings[j][h]]) for h in range(3))
             assert Dw[i, j] == pytest.approx(ww, rel=1e-12, abs=1e-14)
+
+
+@pytest.mark.parametrize("n_rows,n_cols,k", [(50, 50, 5), (300, 300, 20), (64, 1000, 64), (10, 7, 10), (200, 4097, 1)])
+def test_topk_rows_matches_stable_argsort(n_rows, n_cols, k):
+    """hsd_topk_rows == the k first entries of a stable argsort by (distance, column), self excluded;
+    heavy ties on purpose (quantised values)."""
+    import torch
+    from hsd_b200 import engine
+    rng = np.random.default_rng(n_rows * 7 + k)
+    D = np.round(rng.random((n_rows, n_cols)) * 20).astype(np.float32) / 4.0     # many ties, >= 0
+    idx, val = engine.topk_rows(torch.from_numpy(D).cuda(), k)
+    idx, val = idx.cpu().numpy(), val.cpu().numpy()
+    for r in range(n_rows):
+        cand = [j for j in range(n_cols) if j != r]
+        order = sorted(cand, key=lambda j: (D[r, j], j))[:k]
+        want_i = order + [-1] * (k - len(order))
+        assert idx[r].tolist() == want_i
+        assert np.array_equal(val[r, :len(order)], D[r, order])
+        assert np.all(np.isinf(val[r, len(order):]))
+
+
+def test_topk_rows_with_column_mask_and_model_api(golden_graphs):
+    import torch
+    from conftest import nx_graph
+    from hsd_b200 import engine
+    from model import HSD
+    g = nx_graph(golden_graphs, "europe")
+    m = HSD(g, "europe", 0, 3, "wasserstein", signal="degree")
+    D = m.calculate_structural_distance(0.0).astype(np.float32)
+    idx, val = m.nearest_neighbors(10)
+    for r in [0, 100, 398]:
+        order = sorted((j for j in range(m.n_node) if j != r), key=lambda j: (D[r, j], j))[:10]
+        assert idx[r].tolist() == order and np.array_equal(val[r], D[r, order])
+    # neighbours restricted to a "training fold" (even columns)
+    allowed = np.zeros(((m.n_node + 31) // 32) * 32, dtype=np.uint8)
+    allowed[0:m.n_node:2] = 1
+    mask = torch.from_numpy(np.packbits(allowed, bitorder="little").view(np.int32).copy()).cuda()
+    Dd = torch.from_numpy(D).cuda()
+    idx2, _ = engine.topk_rows(Dd, 5, col_mask=mask)
+    idx2 = idx2.cpu().numpy()
+    for r in [1, 50, 397]:
+        order = sorted((j for j in range(0, m.n_node, 2) if j != r), key=lambda j: (D[r, j], j))[:5]
+        assert idx2[r].tolist() == order

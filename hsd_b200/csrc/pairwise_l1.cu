@@ -116,7 +116,7 @@ __device__ __forceinline__ float* row_ptr(const PairArgs& p, int i) {
 #ifndef HSD_PAIR_MINB
 #define HSD_PAIR_MINB 2
 #endif
-template <int UNROLL>
+template <int UNROLL, int KLAST>
 __global__ void __launch_bounds__(PAIR_THREADS, HSD_PAIR_MINB)
 pairwise_l1_kernel(const __grid_constant__ CUtensorMap tmap, const PairArgs p) {
     extern __shared__ __align__(128) unsigned char pair_smem_raw[];
@@ -167,7 +167,10 @@ pairwise_l1_kernel(const __grid_constant__ CUtensorMap tmap, const PairArgs p) {
         for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
 
     uint32_t ready = 0;   // phase of the next chunk already observed complete
-    for (int c = 0; c < p.k_chunks; ++c) {
+    // KLAST > 0: the last chunk holds only KLAST signature rows (the rest is zero padding) and is
+    // peeled off as straight-line code; KLAST == 0: every chunk is full
+    const int full_chunks = KLAST ? p.k_chunks - 1 : p.k_chunks;
+    for (int c = 0; c < full_chunks; ++c) {
         if (tid == 0 && c + LOOKAHEAD < p.k_chunks) issue_chunk(c + LOOKAHEAD);
         const int s = c % STAGES;
         const uint32_t ph = (c / STAGES) & 1;
@@ -203,6 +206,25 @@ pairwise_l1_kernel(const __grid_constant__ CUtensorMap tmap, const PairArgs p) {
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(smem_u32(&sm.empty[s]));
     }
+    if (KLAST) {
+        const int c = full_chunks;
+        const int s = c % STAGES;
+        if (!ready) mbar_wait(smem_u32(&sm.full[s]), (c / STAGES) & 1);
+#pragma unroll
+        for (int kk = 0; kk < KLAST; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&sm.a[s][kk][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&sm.a[s][kk][64 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&sm.b[s][kk][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&sm.b[s][kk][64 + tx * 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) acc[r][q] += fabsf(av[r] - bv[q]);
+        }
+    }
+
     // ===== epilogue: direct store (+ mirrored store for off-diagonal symmetric tiles) =====
     const int row_end = p.row0 + p.n_rows, col_end = p.col0 + p.n_cols;
     const bool full_tile = (i_base + TILE <= row_end) && (j_base + TILE <= col_end) && p.vec_ok;
@@ -322,11 +344,14 @@ static int launch_pairwise(const float* sigT, int32_t k_used, int64_t n_pad, Pai
         HSD_CUDA_TRY(cudaGetLastError());
         return HSD_OK;
     };
-    switch (unroll) {
-        case 4: return launch(pairwise_l1_kernel<4>);
-        case 16: return launch(pairwise_l1_kernel<16>);
-        default: return launch(pairwise_l1_kernel<8>);
-    }
+    static int use_tail = -1;   // HSD_PAIR_TAIL=0 disables the peeled last chunk
+    if (use_tail < 0) { const char* e = getenv("HSD_PAIR_TAIL"); use_tail = e ? atoi(e) : 1; }
+    const int k_last = k_used - (a.k_chunks - 1) * KC;   // 1..KC valid rows in the last chunk
+    if (unroll == 4) return launch(pairwise_l1_kernel<4, 0>);
+    if (unroll == 16) return launch(pairwise_l1_kernel<16, 0>);
+    if (use_tail && k_last <= 4) return launch(pairwise_l1_kernel<8, 4>);
+    if (use_tail && k_last <= 8) return launch(pairwise_l1_kernel<8, 8>);
+    return launch(pairwise_l1_kernel<8, 0>);
 }
 
 }  // namespace hsd

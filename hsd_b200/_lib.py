@@ -58,7 +58,7 @@ lib.hsd_pairwise_worker.argtypes = [_P, _P, _P, _P, _P, c_int32, c_int32, c_int3
                                     c_int32, _P, c_int64, _P]
 lib.hsd_cheb_spmm.argtypes = [_P, _P, c_int32, c_double, _P, c_int32, c_int32, c_int32, c_int32,
                               c_double, _P, _P, _P]
-lib.hsd_ring_reduce.argtypes = [_P, c_int32, c_int32, c_int32, _P, _P, _P, c_int32, c_int32, _P, _P]
+lib.hsd_ring_reduce.argtypes = [_P, c_int32, c_int32, c_int32, _P, _P, _P, c_int32, c_int32, _P, _P, c_int64, _P]
 lib.hsd_characteristic_function.argtypes = [_P, c_int64, c_int32, c_int32, _P, c_int32, _P, _P]
 lib.hsd_topk_rows.argtypes = [_P, c_int64, c_int32, c_int32, c_int32, c_int32, _P, _P, _P, _P]
 lib.hsd_fp32_peak_probe.argtypes = [_P, c_int32, POINTER(c_int64), _P]

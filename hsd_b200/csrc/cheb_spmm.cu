@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(128)
 ring_reduce_kernel(const double* __restrict__ psiT, int n_nodes, int n_cols,
                    const uint32_t* __restrict__ bitmaps, const int32_t* __restrict__ orig_of,
                    int hops1, int n_words, int col0, int v_chunk, int n_scales,
-                   double* __restrict__ emb) {
+                   double* __restrict__ partial) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const int s = blockIdx.z;
     if (c >= n_cols) return;
@@ -160,13 +160,16 @@ ring_reduce_kernel(const double* __restrict__ psiT, int n_nodes, int n_cols,
             }
         }
     }
-    double* dst = emb + (((int64_t)(col0 + c) * n_scales + s) * hops1) * 2;
+    // partial[chunk][c][s][h]: plain stores, summed in chunk order by ring_mean_kernel, so the
+    // result does not depend on scheduling (FP64 atomics would make it vary in the last bits)
+    double* dst = partial + (((int64_t)blockIdx.y * n_cols + c) * n_scales + s) * hops1;
 #pragma unroll
     for (int h = 0; h < RR_MAX_HOPS1; ++h)
-        if (h < hops1 && acc[h] != 0.0) atomicAdd(dst + 2 * h, acc[h]);
+        if (h < hops1) dst[h] = acc[h];
 }
 
-__global__ void ring_mean_kernel(double* emb, const int32_t* __restrict__ sizes, int n_cols,
+__global__ void ring_mean_kernel(double* emb, const double* __restrict__ partial, int chunks,
+                                 const int32_t* __restrict__ sizes, int n_cols,
                                  int col0, int n_scales, int hops1) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int total = n_cols * n_scales * hops1;
@@ -176,7 +179,9 @@ __global__ void ring_mean_kernel(double* emb, const int32_t* __restrict__ sizes,
     const int s = (idx / hops1) % n_scales;
     const int n = sizes[(int64_t)(col0 + c) * hops1 + h];
     double* e = emb + (((int64_t)(col0 + c) * n_scales + s) * hops1 + h) * 2;
-    if (n > 0) e[1] = e[0] / (double)n;
+    double sum = 0.0;
+    for (int k = 0; k < chunks; ++k) sum += partial[(((int64_t)k * n_cols + c) * n_scales + s) * hops1 + h];
+    if (n > 0) { e[0] = sum; e[1] = sum / (double)n; }
     else { e[0] = 0.0; e[1] = 0.0; }
 }
 
@@ -234,25 +239,29 @@ extern "C" int hsd_cheb_spmm(const int32_t* rowptr, const int32_t* col, int32_t 
 extern "C" int hsd_ring_reduce(const double* psiT, int32_t n_scales, int32_t n_nodes, int32_t n_cols,
                                const uint32_t* ring_bitmaps, const int32_t* ring_sizes,
                                const int32_t* orig_of, int32_t hops, int32_t col0, double* emb,
-                               void* stream_) {
+                               double* scratch, int64_t scratch_elems, void* stream_) {
     using namespace hsd;
     cudaStream_t stream = (cudaStream_t)stream_;
-    HSD_REQUIRE(psiT && ring_bitmaps && ring_sizes && emb, "null pointer");
+    HSD_REQUIRE(psiT && ring_bitmaps && ring_sizes && emb && scratch, "null pointer");
     HSD_REQUIRE(n_scales >= 1 && n_nodes > 0 && n_cols > 0 && col0 >= 0 && col0 + n_cols <= n_nodes, "bad sizes");
     HSD_REQUIRE(hops >= 0 && hops + 1 <= RR_MAX_HOPS1, "hops must be <= 7");
     HSD_REQUIRE(n_scales <= 65535, "too many scales");
     const int hops1 = hops + 1, n_words = (n_nodes + 31) / 32;
     // split the node range so the grid has enough CTAs to pull HBM bandwidth
     int chunks = (148 * 8) / (((n_cols + 127) / 128) * n_scales);
+    const int64_t per_chunk = (int64_t)n_cols * n_scales * hops1;
+    HSD_REQUIRE(scratch_elems >= per_chunk, "scratch must hold at least n_cols * n_scales * (hops+1) doubles");
+    if ((int64_t)chunks * per_chunk > scratch_elems) chunks = (int)(scratch_elems / per_chunk);
     chunks = chunks < 1 ? 1 : chunks;
     int v_chunk = ((n_nodes + chunks - 1) / chunks + 31) / 32 * 32;
     chunks = (n_nodes + v_chunk - 1) / v_chunk;
     dim3 grid((n_cols + 127) / 128, chunks, n_scales);
     ring_reduce_kernel<<<grid, 128, 0, stream>>>(psiT, n_nodes, n_cols, ring_bitmaps, orig_of, hops1,
-                                                 n_words, col0, v_chunk, n_scales, emb);
+                                                 n_words, col0, v_chunk, n_scales, scratch);
     HSD_CUDA_TRY(cudaGetLastError());
     const int total = n_cols * n_scales * hops1;
-    ring_mean_kernel<<<(total + 255) / 256, 256, 0, stream>>>(emb, ring_sizes, n_cols, col0, n_scales, hops1);
+    ring_mean_kernel<<<(total + 255) / 256, 256, 0, stream>>>(emb, scratch, chunks, ring_sizes, n_cols, col0,
+                                                              n_scales, hops1);
     HSD_CUDA_TRY(cudaGetLastError());
     return HSD_OK;
 }

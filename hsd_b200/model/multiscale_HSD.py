@@ -19,6 +19,15 @@ from .._lib import check, lib
 from .HSD import HSD
 
 
+def _ring_reduce(psiT, n_scales, n, n_cols, rings, sizes, hops, col0, emb):
+    """hsd_ring_reduce with a workspace sized for ~1000 CTAs of partial sums."""
+    per = n_cols * n_scales * (hops + 1)
+    scratch = torch.empty(per * max(1, min(256, (1 << 24) // max(per, 1))), dtype=torch.float64, device=emb.device)
+    check(lib.hsd_ring_reduce(engine._ptr(psiT), n_scales, n, n_cols, engine._ptr(rings.bitmaps),
+                              engine._ptr(sizes), engine._ptr(rings.orig_of), hops, col0,
+                              engine._ptr(emb), engine._ptr(scratch), scratch.numel(), engine._stream()))
+
+
 class MultiHSD(HSD):
 
     def __init__(self, graph: nx.Graph, graphName: str, hop: int, n_scales: int, metric="euclidean",
@@ -41,9 +50,12 @@ class MultiHSD(HSD):
         super(MultiHSD, self).init()
 
     # ---- batched device path ----
-    def embed_device(self, approx=True, stat="triple") -> torch.Tensor:
-        """emb[N, n_scales, hop+1, 2] float64 = [sum, mean] of Psi_s[i, ring_h(i)]."""
+    def embed_device(self, approx=True, stat="triple", col_range=None) -> torch.Tensor:
+        """emb[N, n_scales, hop+1, 2] float64 = [sum, mean] of Psi_s[i, ring_h(i)].
+        col_range=(begin, end) restricts the work to those nodes' impulse columns (rows of emb
+        outside the range stay zero) — the unit of multi-GPU sharding (embed_device_sharded)."""
         n, hops = self.n_node, self.hop
+        cbeg, cend = (0, n) if col_range is None else col_range
         rings = self._rings()
         scales = [float(s) for s in self.scales]
         dev = self._device()
@@ -61,27 +73,44 @@ class MultiHSD(HSD):
                 work = torch.empty((3, n, cb), dtype=torch.float64, device=dev)
                 out = torch.empty((len(sc), n, cb), dtype=torch.float64, device=dev)
                 part = torch.zeros((n, len(sc), hops + 1, 2), dtype=torch.float64, device=dev)
-                for c0 in range(0, n, cb):
-                    c = min(cb, n - c0)
+                for c0 in range(cbeg, cend, cb):
+                    c = min(cb, cend - c0)
                     w = work.reshape(-1)[:3 * n * c].view(3, n, c)
                     o = out.reshape(-1)[:len(sc) * n * c].view(len(sc), n, c)
                     _wav.cheb_wavelet_block(csr, self.lmax, coeffs, c0, c, thr, w, o)
-                    check(lib.hsd_ring_reduce(engine._ptr(o), len(sc), n, c, engine._ptr(rings.bitmaps),
-                                              engine._ptr(sizes), engine._ptr(rings.orig_of), hops, c0,
-                                              engine._ptr(part), engine._stream()))
+                    _ring_reduce(o, len(sc), n, c, rings, sizes, hops, c0, part)
                 emb[:, s0:s0 + len(sc)] = part
         else:
             L = torch.as_tensor(np.asarray(self.L, dtype=np.float64), device=dev)
             eig = torch.linalg.eigh(L)
+            if col_range is not None:
+                raise ValueError("col_range applies to the Chebyshev path only")
             for si, s in enumerate(scales):
                 psi = _wav.exact_wavelets_dense(L, s, self.THRESHOLD_COEFF, eig)
                 part = torch.zeros((n, 1, hops + 1, 2), dtype=torch.float64, device=dev)
                 psiT = psi.t().contiguous().view(1, n, n)   # psiT[0, v, c] = Psi[c, v]
-                check(lib.hsd_ring_reduce(engine._ptr(psiT), 1, n, n, engine._ptr(rings.bitmaps),
-                                          engine._ptr(sizes), engine._ptr(rings.orig_of), hops, 0,
-                                          engine._ptr(part), engine._stream()))
+                _ring_reduce(psiT, 1, n, n, rings, sizes, hops, 0, part)
                 emb[:, si:si + 1] = part
         return emb
+
+    def embed_device_sharded(self, rank: int, world: int, group=None) -> torch.Tensor:
+        """Multi-GPU embed (SURVEY.md §8 e): every rank owns whole Chebyshev recurrences for a
+        contiguous block of impulse columns (graph and rings replicated), computes the ring
+        statistics of its own nodes, and ONE all-gather of the [N, S, H+1, 2] table replicates
+        the result.  The reference's counterpart is Pool-over-scales with a dense N x N matrix
+        per scale shipped through a pipe (model/multiscale_HSD.py:79-81)."""
+        import torch.distributed as dist
+        n = self.n_node
+        per = ((n + world - 1) // world + 1) // 2 * 2          # even: the SpMM works on column pairs
+        beg, end = min(rank * per, n), min((rank + 1) * per, n)
+        emb = self.embed_device(approx=True, col_range=(beg, end)) if end > beg else None
+        table = torch.zeros((world * per,) + ((len(self.scales), self.hop + 1, 2)), dtype=torch.float64,
+                            device=self._device())
+        if emb is not None:
+            table[beg:end] = emb[beg:end]
+        if world > 1:
+            dist.all_gather_into_tensor(table, table[rank * per:(rank + 1) * per].clone(), group=group)
+        return table[:n]
 
     def _emb_to_dict(self, emb: torch.Tensor, stat: str) -> dict:
         e = emb.cpu().numpy()
@@ -102,9 +131,7 @@ class MultiHSD(HSD):
         dev = self._device()
         row = torch.as_tensor(np.ascontiguousarray(np.asarray(wavelets, dtype=np.float64)[i]), device=dev)
         part = torch.zeros((self.n_node, 1, self.hop + 1, 2), dtype=torch.float64, device=dev)
-        check(lib.hsd_ring_reduce(engine._ptr(row.view(1, self.n_node, 1)), 1, self.n_node, 1,
-                                  engine._ptr(rings.bitmaps), engine._ptr(rings.sizes.contiguous()),
-                                  engine._ptr(rings.orig_of), self.hop, i, engine._ptr(part), engine._stream()))
+        _ring_reduce(row.view(1, self.n_node, 1), 1, self.n_node, 1, rings, rings.sizes.contiguous(), self.hop, i, part)
         return part[i, 0].cpu().numpy()
 
     def get_triple(self, wavelets: np.ndarray, node: str) -> list:

@@ -206,12 +206,14 @@ int hsd_cheb_spmm(const int32_t* rowptr, const int32_t* col, int32_t n_nodes,
  * (double[n_scales][n_nodes][n_cols]).  ring_bitmaps / ring_sizes rows are
  * indexed by the source's ORIGINAL index; bitmap bits are original ids when
  * orig_of == NULL, degree-order ids (mapped through orig_of) otherwise.
- *   emb  double[n_nodes][n_scales][hops+1][2]; rows col0..col0+n_cols-1 must be
- *        zero on entry (sums are accumulated with FP64 atomics, then the mean
- *        is filled in).  hops <= 7. */
+ *   emb      double[n_nodes][n_scales][hops+1][2]; rows col0..col0+n_cols-1 are overwritten
+ *   scratch  double[scratch_elems] workspace, >= n_cols*n_scales*(hops+1); more lets the node
+ *            range be split over more CTAs (partial sums are combined in a fixed order, so
+ *            the result is deterministic).  hops <= 7. */
 int hsd_ring_reduce(const double* psiT, int32_t n_scales, int32_t n_nodes, int32_t n_cols,
                     const uint32_t* ring_bitmaps, const int32_t* ring_sizes,
-                    const int32_t* orig_of, int32_t hops, int32_t col0, double* emb, void* stream);
+                    const int32_t* orig_of, int32_t hops, int32_t col0, double* emb,
+                    double* scratch, int64_t scratch_elems, void* stream);
 
 /* ---- K6: GraphWave characteristic-function embedding --------------------------
  * Replaces model/GraphWave.py:53-69: out[i][2k], out[i][2k+1] = Re, Im of

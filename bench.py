@@ -5,7 +5,8 @@
 
 One "step" = one full pass of the hot path over the workload graph: k-hop rings
 (BFS kernel) -> per-ring degree CDF signatures -> (N>1: one NCCL all-gather of
-the signature table) -> pairwise W1 (L1 between signatures) for this rank's rows.
+the signature table, or peer-memory stores fused into the BFS kernel) -> pairwise W1 (L1
+between signatures) for this rank's share of the symmetric tiles.
 `value` is whole-job unordered node pairs / second with the graph already in HBM;
 `e2e` is the same job through the host-buffer pipeline (pinned host CSR in, pinned
 host float32 matrix out, copies inside the timed region).
@@ -387,9 +388,9 @@ def run_native(args):
                        "l2": "256 MB buffer written before every step (flush) + each step writes a result > L2",
                        "symmetric": world == 1 or peer,
                        "multi_gpu": None if world == 1 else (
-                           "symmetric tiles dealt round-robin to ranks, mirrored into the owners' row blocks "
-                           "through NVLink peer memory (torch symmetric memory); one NCCL all-gather of the "
-                           "signature table" if peer else
+                           "BFS kernel stores each signature row into every rank's table over NVLink peer memory "
+                           "(fused all-gather, no collective); symmetric tiles dealt round-robin to ranks and mirrored "
+                           "into the owners' row blocks through peer memory (torch symmetric memory allocations)" if peer else
                            "independent row blocks (every rank computes rows x all columns); one NCCL all-gather")},
             "stage_ms": {"bfs_signature": bfs_ms, "allgather_transpose": gather_ms, "pairwise": pair_ms},
             "roofline": roofline, "roofline_bfs": roofline_bfs, "cpu_baseline": cpu, "e2e": e2e,

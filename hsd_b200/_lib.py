@@ -13,7 +13,7 @@ from ctypes import c_char_p, c_double, c_float, c_int32, c_int64, c_void_p, POIN
 from .build import LIB
 
 HEADER_SYMBOLS = [
-    "hsd_version", "hsd_last_error_string", "hsd_ring_signature_degree", "hsd_bfs_rings",
+    "hsd_version", "hsd_last_error_string", "hsd_ring_signature_degree", "hsd_ring_signature_degree_allgather", "hsd_bfs_rings",
     "hsd_signature_transpose", "hsd_pairwise_l1", "hsd_pairwise_l1_sharded", "hsd_ring_signature_values",
     "hsd_pairwise_w1_merge", "hsd_pairwise_aligned", "hsd_pairwise_worker", "hsd_cheb_spmm", "hsd_ring_reduce", "hsd_characteristic_function", "hsd_topk_rows",
     "hsd_fp32_peak_probe",
@@ -43,6 +43,8 @@ lib.hsd_version.restype = c_int32
 lib.hsd_last_error_string.restype = c_char_p
 lib.hsd_ring_signature_degree.argtypes = [_P, _P, c_int32, _P, _P, c_int32, c_int32,
                                           _P, _P, c_int32, _P, c_int64, _P, _P, c_int32, _P, _P]
+lib.hsd_ring_signature_degree_allgather.argtypes = [_P, _P, c_int32, _P, _P, c_int32, c_int32, _P, _P, c_int32,
+                                                    _P, c_int64, _P, c_int32, _P, c_int32, _P, _P]
 lib.hsd_bfs_rings.argtypes = [_P, _P, c_int32, _P, _P, c_int32, c_int32, _P, _P, _P]
 lib.hsd_signature_transpose.argtypes = [_P, c_int64, c_int32, c_int32, _P, c_int64, c_int32, _P, _P]
 lib.hsd_pairwise_l1.argtypes = [_P, c_int32, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32,

@@ -32,6 +32,10 @@ struct BfsArgs {
     int32_t n_bins;
     float* sig;
     int64_t sig_ld;
+    // fused all-gather: when set, every signature row is ALSO stored into these peer-mapped
+    // copies of the table (same layout), over NVLink, straight from the kernel that produced it
+    float* const* sig_peers;
+    int32_t n_peers;
     int32_t* ring_sizes;
     uint32_t* ring_bitmaps;
     int32_t empty_as_zero;
@@ -92,7 +96,11 @@ bfs_ring_signature_kernel(const BfsArgs p) {
     if (tid == 0) {
         if (p.ring_sizes) p.ring_sizes[row * hops1] = 1;
         // its W1 term is |deg_i - deg_j|: one scalar instead of a CDF
-        if (p.sig) p.sig[row * p.sig_ld] = (float)(p.rowptr[s + 1] - p.rowptr[s]);
+        if (p.sig) {
+            const float d0 = (float)(p.rowptr[s + 1] - p.rowptr[s]);
+            p.sig[row * p.sig_ld] = d0;
+            for (int r = 0; r < p.n_peers; ++r) p.sig_peers[r][row * p.sig_ld] = d0;
+        }
     }
     __syncthreads();
     if (p.ring_bitmaps) {
@@ -198,20 +206,26 @@ bfs_ring_signature_kernel(const BfsArgs p) {
             for (int w = tid; w < nw; w += THREADS) dst[w] = Fn[w];
         }
         if (p.sig) {
-            float* dst = p.sig + row * p.sig_ld + 1 + (int64_t)(h - 1) * nb1;
+            const int64_t dst_off = row * p.sig_ld + 1 + (int64_t)(h - 1) * nb1;
+            float* dst = p.sig + dst_off;
             if (n_ring > 0) {
                 const float n_f = (float)n_ring;
                 for (int b = tid; b < nb1; b += THREADS) {
                     const int e = __ldg(p.bin_end + b);  // < n_nodes for b < n_bins-1
                     const int cnt = (int)P[e >> 5] + __popc(Fn[e >> 5] & ((1u << (e & 31)) - 1u));
                     // integer count times integer gap, then one IEEE divide (<= 1.5 ulp total)
-                    dst[b] = __fdiv_rn((float)cnt * __ldg(p.delta + b), n_f);
+                    const float val = __fdiv_rn((float)cnt * __ldg(p.delta + b), n_f);
+                    dst[b] = val;
+                    for (int r = 0; r < p.n_peers; ++r) p.sig_peers[r][dst_off + b] = val;
                 }
             } else {
                 if (!p.empty_as_zero && tid == 0) atomicOr(p.status, 1);
                 // empty ring == point mass at 0 (zero padding of tools/metrics.py:18-36): CDF = 1
-                for (int b = tid; b < nb1; b += THREADS)
-                    dst[b] = p.empty_as_zero ? __ldg(p.delta + b) : 0.f;
+                for (int b = tid; b < nb1; b += THREADS) {
+                    const float val = p.empty_as_zero ? __ldg(p.delta + b) : 0.f;
+                    dst[b] = val;
+                    for (int r = 0; r < p.n_peers; ++r) p.sig_peers[r][dst_off + b] = val;
+                }
             }
         }
         n_cur = n_ring;
@@ -252,7 +266,8 @@ static int launch_bfs(const BfsArgs& a, cudaStream_t stream) {
 
 }  // namespace hsd
 
-extern "C" int hsd_ring_signature_degree(const int32_t* rowptr, const int32_t* col, int32_t n_nodes,
+static int ring_signature_degree_impl(float* const* sig_peers, int32_t n_peers,
+                                      const int32_t* rowptr, const int32_t* col, int32_t n_nodes,
                                          const int32_t* src_nodes, const int32_t* out_rows,
                                          int32_t n_src, int32_t hops,
                                          const int32_t* bin_end, const float* delta, int32_t n_bins,
@@ -269,9 +284,35 @@ extern "C" int hsd_ring_signature_degree(const int32_t* rowptr, const int32_t* c
     a.rowptr = rowptr; a.col = col; a.n_nodes = n_nodes; a.n_words = (n_nodes + 31) / 32;
     a.src_nodes = src_nodes; a.out_rows = out_rows; a.n_src = n_src; a.hops = hops;
     a.bin_end = bin_end; a.delta = delta; a.n_bins = sig ? n_bins : 1;
-    a.sig = sig; a.sig_ld = sig_ld; a.ring_sizes = ring_sizes; a.ring_bitmaps = ring_bitmaps;
+    a.sig = sig; a.sig_ld = sig_ld; a.sig_peers = sig_peers; a.n_peers = n_peers; a.ring_sizes = ring_sizes; a.ring_bitmaps = ring_bitmaps;
     a.empty_as_zero = empty_as_zero; a.status = status;
     return hsd::launch_bfs(a, (cudaStream_t)stream);
+}
+
+extern "C" int hsd_ring_signature_degree(const int32_t* rowptr, const int32_t* col, int32_t n_nodes,
+                                         const int32_t* src_nodes, const int32_t* out_rows,
+                                         int32_t n_src, int32_t hops,
+                                         const int32_t* bin_end, const float* delta, int32_t n_bins,
+                                         float* sig, int64_t sig_ld, int32_t* ring_sizes,
+                                         uint32_t* ring_bitmaps, int32_t empty_as_zero,
+                                         int32_t* status, void* stream) {
+    return ring_signature_degree_impl(nullptr, 0, rowptr, col, n_nodes, src_nodes, out_rows, n_src, hops, bin_end,
+                                      delta, n_bins, sig, sig_ld, ring_sizes, ring_bitmaps, empty_as_zero,
+                                      status, stream);
+}
+
+extern "C" int hsd_ring_signature_degree_allgather(const int32_t* rowptr, const int32_t* col, int32_t n_nodes,
+                                                   const int32_t* src_nodes, const int32_t* out_rows,
+                                                   int32_t n_src, int32_t hops, const int32_t* bin_end,
+                                                   const float* delta, int32_t n_bins, float* sig,
+                                                   int64_t sig_ld, float* const* sig_peers, int32_t n_peers,
+                                                   int32_t* ring_sizes, int32_t empty_as_zero,
+                                                   int32_t* status, void* stream) {
+    HSD_REQUIRE(sig && (n_peers == 0 || sig_peers), "fused all-gather needs the local table and the peer pointer array");
+    HSD_REQUIRE(n_peers >= 0 && n_peers <= 64, "bad n_peers");
+    return ring_signature_degree_impl(sig_peers, n_peers, rowptr, col, n_nodes, src_nodes, out_rows, n_src, hops,
+                                      bin_end, delta, n_bins, sig, sig_ld, ring_sizes, nullptr, empty_as_zero,
+                                      status, stream);
 }
 
 extern "C" int hsd_bfs_rings(const int32_t* rowptr, const int32_t* col, int32_t n_nodes,

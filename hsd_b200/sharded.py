@@ -33,12 +33,17 @@ class ShardedDegreeHSD:
     """Plan + buffers for repeated evaluation of one graph on `world` ranks."""
 
     def __init__(self, dg: engine.DeviceGraph, hops: int, rank: int = 0, world: int = 1,
-                 group=None, empty: str = "raise", peer: bool = False, peer_blocks=None):
+                 group=None, empty: str = "raise", peer: bool = False, peer_blocks=None,
+                 peer_tables=None):
         """peer=True (world > 1): the result blocks are allocated as symmetric memory and mapped
         into every rank over NVLink; the pairwise kernel then computes each symmetric tile once
         in the whole job and stores its mirror straight into the owner's block
         (hsd_pairwise_l1_sharded).  peer=False: every rank computes its full row block.
-        peer_blocks: list of `world` local tensors standing in for the peers' blocks (tests)."""
+        The signature table is symmetric memory as well and the BFS kernel stores every row it
+        produces into all ranks' copies (hsd_ring_signature_degree_allgather), so no collective is
+        issued at all — only two barriers per step.
+        peer_blocks / peer_tables: lists of `world` local tensors standing in for the peers'
+        result blocks / signature tables (single-GPU emulation in the tests)."""
         self.dg, self.hops, self.rank, self.world, self.group, self.empty = dg, hops, rank, world, group, empty
         n = dg.n
         dev = dg.rowptr.device
@@ -46,7 +51,25 @@ class ShardedDegreeHSD:
         self.k_used = dg.k_used(hops)
         self.ld = engine.roundup(self.k_used, 4)
         # row-major signature table, padded to world * per rows so every rank's chunk is equal
-        self.sig_all = torch.zeros((world * self.per, self.ld), dtype=torch.float32, device=dev)
+        self.peer = bool(peer) and world > 1
+        self.sig_symm = None
+        self.sig_peer_ptrs = None
+        if self.peer and peer_tables is not None:
+            self.sig_all = peer_tables[rank]
+            self.sig_peer_ptrs = torch.tensor([t.data_ptr() for r, t in enumerate(peer_tables) if r != rank],
+                                              dtype=torch.int64, device=dev)
+        elif self.peer and peer_blocks is None:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm_mem
+            self.sig_all = symm_mem.empty((world * self.per, self.ld), dtype=torch.float32, device=dev)
+            self.sig_all.zero_()
+            self.sig_symm = symm_mem.rendezvous(self.sig_all, group if group is not None else dist.group.WORLD)
+            self.sig_peer_ptrs = torch.tensor([int(p) for r, p in enumerate(self.sig_symm.buffer_ptrs) if r != rank],
+                                              dtype=torch.int64, device=dev)
+            torch.cuda.synchronize(dev)
+            dist.barrier(group=group)      # every table is zeroed before any peer may store into it
+        else:
+            self.sig_all = torch.zeros((world * self.per, self.ld), dtype=torch.float32, device=dev)
         self.sigT = engine.alloc_signature_table(self.k_used, n, dev)
         # BFS sources are DEALT round-robin (node s -> rank s % world): contiguous blocks would give
         # one rank all the hubs of a preferential-attachment graph (its BFS then takes 2x longer).
@@ -60,7 +83,6 @@ class ShardedDegreeHSD:
         self.sizes = torch.zeros((world * self.per, hops + 1), dtype=torch.int32, device=dev)
         self.status = torch.zeros(1, dtype=torch.int32, device=dev)
         self.launches_per_step = 3
-        self.peer = bool(peer) and world > 1
         self.symm = None
         self.ld_out = engine.roundup(n, 4)
         if self.peer and peer_blocks is not None:
@@ -89,6 +111,15 @@ class ShardedDegreeHSD:
         dg = self.dg
         if self.n_src == 0:
             return
+        if self.sig_peer_ptrs is not None:
+            check(lib.hsd_ring_signature_degree_allgather(
+                engine._ptr(dg.rowptr), engine._ptr(dg.col), dg.n, engine._ptr(self.src),
+                engine._ptr(self.out_rows), self.n_src, self.hops,
+                engine._ptr(dg.bin_end), engine._ptr(dg.delta), dg.n_bins,
+                engine._ptr(self.sig_all), self.ld, engine._ptr(self.sig_peer_ptrs),
+                int(self.sig_peer_ptrs.numel()), engine._ptr(self.sizes),
+                1 if self.empty == "zero" else 0, engine._ptr(self.status), engine._stream()))
+            return
         check(lib.hsd_ring_signature_degree(
             engine._ptr(dg.rowptr), engine._ptr(dg.col), dg.n, engine._ptr(self.src),
             engine._ptr(self.out_rows), self.n_src, self.hops,
@@ -99,6 +130,11 @@ class ShardedDegreeHSD:
     def gather(self) -> None:
         """The one collective: in-place all-gather of the signature table (NCCL over NVLink)."""
         if self.world == 1:
+            return
+        if self.sig_peer_ptrs is not None:
+            # the rows were already stored into every rank's table by the BFS kernel: only wait
+            if self.sig_symm is not None:
+                self.sig_symm.barrier()
             return
         import torch.distributed as dist
         chunk = self.sig_all[self.rank * self.per:(self.rank + 1) * self.per]

@@ -79,6 +79,19 @@ int hsd_ring_signature_degree(const int32_t* rowptr, const int32_t* col, int32_t
                               int32_t* ring_sizes, uint32_t* ring_bitmaps,
                               int32_t empty_as_zero, int32_t* status, void* stream);
 
+/* Same kernel with the all-gather of the signature table fused in: every signature row is
+ * stored into the local table AND into n_peers peer-mapped copies of it (sig_peers: DEVICE
+ * array of n_peers base pointers, same layout; NVLink peer memory) as it is produced, so the
+ * ranks of a sharded run need no collective afterwards — only a barrier.  The reference's
+ * counterpart is pickling the whole model into every Pool task (model/HSD.py:122-124). */
+int hsd_ring_signature_degree_allgather(const int32_t* rowptr, const int32_t* col, int32_t n_nodes,
+                                        const int32_t* src_nodes, const int32_t* out_rows, int32_t n_src,
+                                        int32_t hops, const int32_t* bin_end, const float* delta,
+                                        int32_t n_bins, float* sig, int64_t sig_ld,
+                                        float* const* sig_peers, int32_t n_peers,
+                                        int32_t* ring_sizes, int32_t empty_as_zero, int32_t* status,
+                                        void* stream);
+
 /* Rings only (tools/hierarchy.py:25-38, model/HSD.py:87-94 ring sizes). */
 int hsd_bfs_rings(const int32_t* rowptr, const int32_t* col, int32_t n_nodes,
                   const int32_t* src_nodes, const int32_t* out_rows, int32_t n_src,

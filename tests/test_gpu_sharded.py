@@ -56,6 +56,22 @@ def test_emulated_peer_memory_symmetric_tiles(world, n):
     torch.cuda.synchronize()
     got = torch.cat([b[:, :n] for b in blocks], 0)[:n]
     assert torch.equal(got, single)
+    # fused all-gather: the BFS kernel of every "rank" stores its rows into all tables itself
+    k_ld = plans[0].ld
+    tables = [torch.zeros((world * per, k_ld), dtype=torch.float32, device="cuda") for _ in range(world)]
+    blocks2 = [torch.full((per, ld), float("nan"), dtype=torch.float32, device="cuda") for _ in range(world)]
+    fused = [ShardedDegreeHSD(dg, 3, r, world, peer=True, peer_blocks=blocks2, peer_tables=tables)
+             for r in range(world)]
+    for p in fused:
+        p.signatures()
+    torch.cuda.synchronize()
+    for t in tables[1:]:
+        assert torch.equal(t, tables[0])
+    assert torch.equal(tables[0], plans[0].sig_all)
+    for p in fused:
+        p.distances()
+    torch.cuda.synchronize()
+    assert torch.equal(torch.cat([b[:, :n] for b in blocks2], 0)[:n], single)
 
 
 def test_host_pipeline_matches_device_path():

@@ -207,6 +207,28 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Restrict this process to the CPUs NVML reports as local to GPU `index`, so that pinned
+    host buffers (first touch) and the copy threads sit on the socket the GPU's PCIe link hangs
+    off.  With 4-8 ranks streaming results to the host at once, remote-socket buffers otherwise
+    halve the device-to-host rate.  Best effort: returns the CPU count bound, or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_cpu = os.cpu_count() or 1
+        words = (n_cpu + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {w * 64 + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 # ------------------------------------------------------------------------------
 # native arm
 # ------------------------------------------------------------------------------
@@ -224,6 +246,7 @@ def run_native(args):
         raise SystemExit("bench.py (native arm) needs a CUDA device: hsd_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)   # pinned host buffers then land on the GPU's own socket
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -367,6 +390,7 @@ def run_native(args):
     e2e = {"value": pairs / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": int(pipe.h2d_bytes), "d2h_bytes_per_step": int(pipe.d2h_bytes),
            "api": "hsd_b200.engine.HostDegreePipeline.run (what HSD.calculate_structural_distance(out=pinned) calls)",
+           "cpus_bound_to_gpu_numa_node": numa,
            "checksum": float(host_out[: min(64, pipe.n_rows)].double().sum().item())}
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ----

@@ -42,9 +42,9 @@ _P = c_void_p
 lib.hsd_version.restype = c_int32
 lib.hsd_last_error_string.restype = c_char_p
 lib.hsd_ring_signature_degree.argtypes = [_P, _P, c_int32, _P, _P, c_int32, c_int32,
-                                          _P, _P, c_int32, _P, c_int64, _P, _P, c_int32, _P, _P]
+                                          _P, _P, c_int32, _P, c_int64, _P, _P, c_int32, _P, c_int32, _P]
 lib.hsd_ring_signature_degree_allgather.argtypes = [_P, _P, c_int32, _P, _P, c_int32, c_int32, _P, _P, c_int32,
-                                                    _P, c_int64, _P, c_int32, _P, c_int32, _P, _P]
+                                                    _P, c_int64, _P, c_int32, _P, c_int32, _P, c_int32, _P]
 lib.hsd_bfs_rings.argtypes = [_P, _P, c_int32, _P, _P, c_int32, c_int32, _P, _P, _P]
 lib.hsd_signature_transpose.argtypes = [_P, c_int64, c_int32, c_int32, _P, c_int64, c_int32, _P, _P]
 lib.hsd_pairwise_l1.argtypes = [_P, c_int32, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32,

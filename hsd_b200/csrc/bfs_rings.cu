@@ -40,6 +40,7 @@ struct BfsArgs {
     uint32_t* ring_bitmaps;
     int32_t empty_as_zero;
     int32_t* status;
+    int32_t cta_threads;   // 0 = choose from the graph size
 };
 
 // `seen` = every node discovered so far (all earlier rings + the part of the current ring found
@@ -246,11 +247,15 @@ static int launch_bfs(const BfsArgs& a, cudaStream_t stream) {
     // small graphs: per-level fixed costs (barriers, scans) dominate, so use small CTAs and more of them
     static int force = -1;   // tuning knob: HSD_BFS_THREADS in {128, 256, 512}
     if (force < 0) { const char* e = getenv("HSD_BFS_THREADS"); force = e ? atoi(e) : 0; }
-    const int threads = force ? force : (a.n_nodes > 48 * 1024 ? 512 : 256);
+    const int threads = a.cta_threads ? a.cta_threads : (force ? force : (a.n_nodes > 48 * 1024 ? 512 : 256));
     if (threads == 128) {
         HSD_CUDA_TRY(cudaFuncSetAttribute(bfs_ring_signature_kernel<128>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         bfs_ring_signature_kernel<128><<<a.n_src, 128, smem, stream>>>(a);
+    } else if (threads == 1024) {
+        HSD_CUDA_TRY(cudaFuncSetAttribute(bfs_ring_signature_kernel<1024>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        bfs_ring_signature_kernel<1024><<<a.n_src, 1024, smem, stream>>>(a);
     } else if (threads == 512) {
         HSD_CUDA_TRY(cudaFuncSetAttribute(bfs_ring_signature_kernel<512>,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -273,8 +278,10 @@ static int ring_signature_degree_impl(float* const* sig_peers, int32_t n_peers,
                                          const int32_t* bin_end, const float* delta, int32_t n_bins,
                                          float* sig, int64_t sig_ld, int32_t* ring_sizes,
                                          uint32_t* ring_bitmaps, int32_t empty_as_zero,
-                                         int32_t* status, void* stream) {
+                                         int32_t* status, int32_t cta_threads, void* stream) {
     HSD_REQUIRE(rowptr && col && src_nodes && out_rows, "null graph/source pointer");
+    HSD_REQUIRE(cta_threads == 0 || cta_threads == 128 || cta_threads == 256 || cta_threads == 512 ||
+                    cta_threads == 1024, "cta_threads must be 0 (auto), 128, 256, 512 or 1024");
     HSD_REQUIRE(n_nodes > 0 && n_src >= 0 && hops >= 0, "bad sizes");
     if (sig) {
         HSD_REQUIRE(bin_end && delta && n_bins >= 1 && status, "sig requested without support tables");
@@ -285,7 +292,7 @@ static int ring_signature_degree_impl(float* const* sig_peers, int32_t n_peers,
     a.src_nodes = src_nodes; a.out_rows = out_rows; a.n_src = n_src; a.hops = hops;
     a.bin_end = bin_end; a.delta = delta; a.n_bins = sig ? n_bins : 1;
     a.sig = sig; a.sig_ld = sig_ld; a.sig_peers = sig_peers; a.n_peers = n_peers; a.ring_sizes = ring_sizes; a.ring_bitmaps = ring_bitmaps;
-    a.empty_as_zero = empty_as_zero; a.status = status;
+    a.empty_as_zero = empty_as_zero; a.status = status; a.cta_threads = cta_threads;
     return hsd::launch_bfs(a, (cudaStream_t)stream);
 }
 
@@ -295,10 +302,10 @@ extern "C" int hsd_ring_signature_degree(const int32_t* rowptr, const int32_t* c
                                          const int32_t* bin_end, const float* delta, int32_t n_bins,
                                          float* sig, int64_t sig_ld, int32_t* ring_sizes,
                                          uint32_t* ring_bitmaps, int32_t empty_as_zero,
-                                         int32_t* status, void* stream) {
+                                         int32_t* status, int32_t cta_threads, void* stream) {
     return ring_signature_degree_impl(nullptr, 0, rowptr, col, n_nodes, src_nodes, out_rows, n_src, hops, bin_end,
                                       delta, n_bins, sig, sig_ld, ring_sizes, ring_bitmaps, empty_as_zero,
-                                      status, stream);
+                                      status, cta_threads, stream);
 }
 
 extern "C" int hsd_ring_signature_degree_allgather(const int32_t* rowptr, const int32_t* col, int32_t n_nodes,
@@ -307,12 +314,12 @@ extern "C" int hsd_ring_signature_degree_allgather(const int32_t* rowptr, const 
                                                    const float* delta, int32_t n_bins, float* sig,
                                                    int64_t sig_ld, float* const* sig_peers, int32_t n_peers,
                                                    int32_t* ring_sizes, int32_t empty_as_zero,
-                                                   int32_t* status, void* stream) {
+                                                   int32_t* status, int32_t cta_threads, void* stream) {
     HSD_REQUIRE(sig && (n_peers == 0 || sig_peers), "fused all-gather needs the local table and the peer pointer array");
     HSD_REQUIRE(n_peers >= 0 && n_peers <= 64, "bad n_peers");
     return ring_signature_degree_impl(sig_peers, n_peers, rowptr, col, n_nodes, src_nodes, out_rows, n_src, hops,
                                       bin_end, delta, n_bins, sig, sig_ld, ring_sizes, nullptr, empty_as_zero,
-                                      status, stream);
+                                      status, cta_threads, stream);
 }
 
 extern "C" int hsd_bfs_rings(const int32_t* rowptr, const int32_t* col, int32_t n_nodes,
@@ -321,5 +328,5 @@ extern "C" int hsd_bfs_rings(const int32_t* rowptr, const int32_t* col, int32_t 
                              uint32_t* ring_bitmaps, void* stream) {
     return hsd_ring_signature_degree(rowptr, col, n_nodes, src_nodes, out_rows, n_src, hops,
                                      nullptr, nullptr, 1, nullptr, 0, ring_sizes,
-                                     ring_bitmaps, 1, nullptr, stream);
+                                     ring_bitmaps, 1, nullptr, 0, stream);
 }

@@ -130,7 +130,7 @@ def ring_signature_degree(dg: DeviceGraph, hops: int, rows: Optional[torch.Tenso
         _ptr(dg.rowptr), _ptr(dg.col), dg.n, _ptr(src), _ptr(out_rows), n_src, hops,
         _ptr(dg.bin_end), _ptr(dg.delta), dg.n_bins,
         _ptr(sig), ld, _ptr(sizes), _ptr(bitmaps), 1 if empty == "zero" else 0,
-        _ptr(status), _stream()))
+        _ptr(status), 0, _stream()))
     return sig, sizes, bitmaps, status
 
 
@@ -312,7 +312,7 @@ class HostDegreePipeline:
             _ptr(d["rowptr"]), _ptr(d["col"]), self.n, _ptr(d["new_of"]), _ptr(self.out_rows_idx), self.n,
             self.hops, _ptr(d["bin_end"]), _ptr(d["delta"]), self.n_bins,
             _ptr(self.sig), self.sig.stride(0), None, None, 1 if self.empty == "zero" else 0,
-            _ptr(self.status), _stream()))
+            _ptr(self.status), 0, _stream()))
         signature_transpose(self.sig, self.k_used, self.sigT, 0)
         for (p0, pr) in self.panels:
             if self.full:

@@ -20,6 +20,9 @@ import torch
 from . import engine
 
 
+HUB_DEGREE = 64
+
+
 def shard_rows(n: int, world: int, rank: int) -> Tuple[int, int, int]:
     """(row0, n_rows, rows_per_rank): contiguous blocks of ceil(n / world) rows rounded up to
     a multiple of 4 (the pairwise kernel's TMA tile origins must be 16-byte aligned), the last
@@ -78,6 +81,18 @@ class ShardedDegreeHSD:
         self.n_src = int(self.rows.numel())
         self.src = dg.new_of[self.rows.long()].contiguous()
         self.out_rows = (rank * self.per + torch.arange(self.n_src, dtype=torch.int32, device=dev)).contiguous()
+        # Latency regime (few sources per rank): one hub source is latency-bound inside its CTA and sets
+        # the floor of the whole BFS phase, so hubs (degree > HUB_DEGREE) get 1024-thread CTAs on a side
+        # stream while the rest run with the default CTA size.
+        self.side = None
+        self.hub_split = None
+        if 0 < self.n_src <= 4096:
+            deg = (dg.rowptr[1:] - dg.rowptr[:-1])[self.src.long()]
+            hub = deg > HUB_DEGREE
+            if bool(hub.any()) and not bool(hub.all()):
+                self.hub_split = (self.src[hub].contiguous(), self.out_rows[hub].contiguous(),
+                                  self.src[~hub].contiguous(), self.out_rows[~hub].contiguous())
+                self.side = torch.cuda.Stream(device=dev)
         node = torch.arange(n, dtype=torch.int32, device=dev)
         self.table_row = ((node % world) * self.per + node // world).to(torch.int32).contiguous()
         self.sizes = torch.zeros((world * self.per, hops + 1), dtype=torch.int32, device=dev)
@@ -111,21 +126,33 @@ class ShardedDegreeHSD:
         dg = self.dg
         if self.n_src == 0:
             return
-        if self.sig_peer_ptrs is not None:
-            check(lib.hsd_ring_signature_degree_allgather(
-                engine._ptr(dg.rowptr), engine._ptr(dg.col), dg.n, engine._ptr(self.src),
-                engine._ptr(self.out_rows), self.n_src, self.hops,
-                engine._ptr(dg.bin_end), engine._ptr(dg.delta), dg.n_bins,
-                engine._ptr(self.sig_all), self.ld, engine._ptr(self.sig_peer_ptrs),
-                int(self.sig_peer_ptrs.numel()), engine._ptr(self.sizes),
-                1 if self.empty == "zero" else 0, engine._ptr(self.status), engine._stream()))
+
+        def launch(src, out_rows, threads, stream):
+            if self.sig_peer_ptrs is not None:
+                check(lib.hsd_ring_signature_degree_allgather(
+                    engine._ptr(dg.rowptr), engine._ptr(dg.col), dg.n, engine._ptr(src),
+                    engine._ptr(out_rows), int(src.numel()), self.hops,
+                    engine._ptr(dg.bin_end), engine._ptr(dg.delta), dg.n_bins,
+                    engine._ptr(self.sig_all), self.ld, engine._ptr(self.sig_peer_ptrs),
+                    int(self.sig_peer_ptrs.numel()), engine._ptr(self.sizes),
+                    1 if self.empty == "zero" else 0, engine._ptr(self.status), threads, stream))
+            else:
+                check(lib.hsd_ring_signature_degree(
+                    engine._ptr(dg.rowptr), engine._ptr(dg.col), dg.n, engine._ptr(src),
+                    engine._ptr(out_rows), int(src.numel()), self.hops,
+                    engine._ptr(dg.bin_end), engine._ptr(dg.delta), dg.n_bins,
+                    engine._ptr(self.sig_all), self.ld, engine._ptr(self.sizes), None,
+                    1 if self.empty == "zero" else 0, engine._ptr(self.status), threads, stream))
+
+        if self.hub_split is None:
+            launch(self.src, self.out_rows, 0, engine._stream())
             return
-        check(lib.hsd_ring_signature_degree(
-            engine._ptr(dg.rowptr), engine._ptr(dg.col), dg.n, engine._ptr(self.src),
-            engine._ptr(self.out_rows), self.n_src, self.hops,
-            engine._ptr(dg.bin_end), engine._ptr(dg.delta), dg.n_bins,
-            engine._ptr(self.sig_all), self.ld, engine._ptr(self.sizes), None,
-            1 if self.empty == "zero" else 0, engine._ptr(self.status), engine._stream()))
+        hub_src, hub_rows, rest_src, rest_rows = self.hub_split
+        cur = torch.cuda.current_stream()
+        self.side.wait_stream(cur)
+        launch(hub_src, hub_rows, 1024, self.side.cuda_stream)
+        launch(rest_src, rest_rows, 0, cur.cuda_stream)
+        cur.wait_stream(self.side)
 
     def gather(self) -> None:
         """The one collective: in-place all-gather of the signature table (NCCL over NVLink)."""

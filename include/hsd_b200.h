@@ -70,6 +70,9 @@ const char* hsd_last_error_string(void);
  *   empty_as_zero                 0: an empty ring sets *status |= 1 (caller raises, like scipy);
  *                                 1: an empty ring is the point mass at 0 (tools/metrics.py:18-36 padding)
  *   status                        int32[1], OR-ed flags, caller zeroes it
+ *   cta_threads                   0 = pick from the graph size; 128/256/512/1024 to override (one hub
+ *                                 source is latency-bound inside its CTA: hubs finish ~2x sooner with 1024
+ *                                 threads, low-degree sources run best with 256)
  */
 int hsd_ring_signature_degree(const int32_t* rowptr, const int32_t* col, int32_t n_nodes,
                               const int32_t* src_nodes, const int32_t* out_rows, int32_t n_src,
@@ -77,7 +80,7 @@ int hsd_ring_signature_degree(const int32_t* rowptr, const int32_t* col, int32_t
                               const int32_t* bin_end, const float* delta, int32_t n_bins,
                               float* sig, int64_t sig_ld,
                               int32_t* ring_sizes, uint32_t* ring_bitmaps,
-                              int32_t empty_as_zero, int32_t* status, void* stream);
+                              int32_t empty_as_zero, int32_t* status, int32_t cta_threads, void* stream);
 
 /* Same kernel with the all-gather of the signature table fused in: every signature row is
  * stored into the local table AND into n_peers peer-mapped copies of it (sig_peers: DEVICE
@@ -90,7 +93,7 @@ int hsd_ring_signature_degree_allgather(const int32_t* rowptr, const int32_t* co
                                         int32_t n_bins, float* sig, int64_t sig_ld,
                                         float* const* sig_peers, int32_t n_peers,
                                         int32_t* ring_sizes, int32_t empty_as_zero, int32_t* status,
-                                        void* stream);
+                                        int32_t cta_threads, void* stream);
 
 /* Rings only (tools/hierarchy.py:25-38, model/HSD.py:87-94 ring sizes). */
 int hsd_bfs_rings(const int32_t* rowptr, const int32_t* col, int32_t n_nodes,

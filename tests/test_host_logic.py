@@ -32,7 +32,7 @@ def test_c_abi_argument_validation_without_gpu():
     assert lib.hsd_pairwise_l1(p, 16, 128, 0, 64, 0, 32, 1, p, 128, None) == -1   # symmetric trapezoid
     assert lib.hsd_pairwise_l1(p, 16, 128, 2, 64, 0, 32, 0, p, 128, None) == -1   # TMA origin alignment
     assert lib.hsd_ring_signature_degree(None, None, 4, None, None, 1, 2, None, None, 1, None, 0,
-                                         None, None, 0, None, None) == -1
+                                         None, None, 0, None, 0, None) == -1
     assert lib.hsd_pairwise_aligned(p, p, p, 4, 2, 0, 3, 7, 0, 1, p, 4, None) == -1  # metric id
     assert lib.hsd_ring_reduce(p, 1, 4, 4, p, p, None, 9, 0, p, p, 64, None) == -1   # hops > 7
     with pytest.raises(HSDError):

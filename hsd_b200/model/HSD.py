@@ -142,13 +142,14 @@ class HSD(object):
             self.construct_hierarchy()
 
     def construct_hierarchy(self):
-        """Alias used by main.py:15: build the k-hop rings with the BFS kernel.  The dict
-        form (``model.hierarchy``) is materialised from the device bitmaps on first read."""
+        """Alias used by main.py:15: (re)build the k-hop rings with the BFS kernel.  Lazy: the
+        kernel runs when the rings are first needed, and the dict form (``model.hierarchy``) is
+        materialised from the device bitmaps on first read — the degree-signal path never needs
+        the ring bitmaps at all (they are 6 GB at N = 100k, hop 4)."""
         self._hierarchy = None
         self._ringset = None
         self._ringset_src = None
-        self._rings()
-        self._hierarchy_lazy = True
+        self._hierarchy_lazy = True   # the BFS runs on first use (distances / embeddings / model.hierarchy)
 
     # ---- wavelets (model/HSD.py:48-67) ----
     def _wavelets_device(self, scale, approx=True) -> torch.Tensor:

@@ -15,7 +15,7 @@ from .build import LIB
 HEADER_SYMBOLS = [
     "hsd_version", "hsd_last_error_string", "hsd_ring_signature_degree", "hsd_ring_signature_degree_allgather", "hsd_bfs_rings",
     "hsd_signature_transpose", "hsd_pairwise_l1", "hsd_pairwise_l1_sharded", "hsd_ring_signature_values",
-    "hsd_pairwise_w1_merge", "hsd_pairwise_aligned", "hsd_pairwise_worker", "hsd_cheb_spmm", "hsd_ring_reduce", "hsd_characteristic_function", "hsd_topk_rows",
+    "hsd_pairwise_w1_merge", "hsd_pairwise_aligned", "hsd_pairwise_worker", "hsd_cheb_spmm", "hsd_laplacian_spmv", "hsd_ring_reduce", "hsd_characteristic_function", "hsd_topk_rows",
     "hsd_fp32_peak_probe",
 ]
 
@@ -60,6 +60,7 @@ lib.hsd_pairwise_worker.argtypes = [_P, _P, _P, _P, _P, c_int32, c_int32, c_int3
                                     c_int32, _P, c_int64, _P]
 lib.hsd_cheb_spmm.argtypes = [_P, _P, c_int32, c_double, _P, c_int32, c_int32, c_int32, c_int32,
                               c_double, _P, _P, _P]
+lib.hsd_laplacian_spmv.argtypes = [_P, _P, c_int32, _P, _P, _P]
 lib.hsd_ring_reduce.argtypes = [_P, c_int32, c_int32, c_int32, _P, _P, _P, c_int32, c_int32, _P, _P, c_int64, _P]
 lib.hsd_characteristic_function.argtypes = [_P, c_int64, c_int32, c_int32, _P, c_int32, _P, _P]
 lib.hsd_topk_rows.argtypes = [_P, c_int64, c_int32, c_int32, c_int32, c_int32, _P, _P, _P, _P]

@@ -113,6 +113,29 @@ __global__ void __launch_bounds__(256) cheb_step_kernel(const ChebArgs p) {
     }
 }
 
+// y = L x for one vector (L = D - A from the CSR, self-loops cancel): one warp per row.  Used by the
+// lmax estimate (power iteration), the device counterpart of pygsp's Graph.estimate_lmax.
+__global__ void __launch_bounds__(256)
+laplacian_spmv_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int n,
+                      const double* __restrict__ x, double* __restrict__ y) {
+    const int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (v >= n) return;
+    const int e0 = __ldg(rowptr + v), e1 = __ldg(rowptr + v + 1);
+    double nb = 0.0;
+    int deg = 0;
+    for (int e = e0 + lane; e < e1; e += 32) {
+        const int u = __ldg(col + e);
+        if (u != v) { nb += x[u]; ++deg; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        nb += __shfl_down_sync(0xffffffffu, nb, o);
+        deg += __shfl_down_sync(0xffffffffu, deg, o);
+    }
+    if (lane == 0) y[v] = (double)deg * x[v] - nb;
+}
+
 // order == 0 degenerate case: R = c0/2 * E (+ threshold)
 __global__ void cheb_order0_kernel(const double* t0, double* out, int64_t n, double c0, double thr) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -262,6 +285,16 @@ extern "C" int hsd_ring_reduce(const double* psiT, int32_t n_scales, int32_t n_n
     const int total = n_cols * n_scales * hops1;
     ring_mean_kernel<<<(total + 255) / 256, 256, 0, stream>>>(emb, scratch, chunks, ring_sizes, n_cols, col0,
                                                               n_scales, hops1);
+    HSD_CUDA_TRY(cudaGetLastError());
+    return HSD_OK;
+}
+
+extern "C" int hsd_laplacian_spmv(const int32_t* rowptr, const int32_t* col, int32_t n_nodes,
+                                  const double* x, double* y, void* stream) {
+    using namespace hsd;
+    HSD_REQUIRE(rowptr && col && x && y && n_nodes > 0, "bad arguments");
+    const int64_t threads = (int64_t)n_nodes * 32;
+    laplacian_spmv_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rowptr, col, n_nodes, x, y);
     HSD_CUDA_TRY(cudaGetLastError());
     return HSD_OK;
 }

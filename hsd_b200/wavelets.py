@@ -32,10 +32,39 @@ def cheby_coefficients(scale: float, lmax: float, order: int) -> np.ndarray:
     return (2.0 / n) * (np.cos(k * theta[None, :]) @ g)
 
 
-def estimate_lmax(g: CSRGraph) -> float:
-    """pygsp Graph.estimate_lmax: 1.01 x the largest Laplacian eigenvalue from
-    ARPACK (k=1, tol=5e-3, ncv=min(N,10)); call sites model/HSD.py:51,
-    model/multiscale_HSD.py:28.  A fixed-seed start vector makes it reproducible."""
+def estimate_lmax(g: CSRGraph, device=None, tol: float = 1e-6, max_iter: int = 2000) -> float:
+    """1.01 x the largest Laplacian eigenvalue — what pygsp's Graph.estimate_lmax returns
+    (ARPACK there, tol 5e-3; call sites model/HSD.py:51, model/multiscale_HSD.py:28) — by
+    power iteration on the device (hsd_laplacian_spmv + a Rayleigh quotient), FP64, fixed start
+    vector, stopped when the eigenvalue estimate moves by less than `tol` relative.  pygsp's own
+    value is only reproducible to ~2 digits, so parity tests pass lmax explicitly to both sides."""
+    dev = device or engine.require_cuda()
+    csr = DeviceCSR(g, dev)
+    n = g.n
+    if n == 1:
+        return 0.0
+    # deterministic, not orthogonal to the top eigenvector in practice: degree-weighted alternating signs
+    x = torch.from_numpy((np.diff(g.rowptr).astype(np.float64) + 1.0) * np.where(np.arange(n) % 2, -1.0, 1.0)).to(dev)
+    x /= torch.linalg.vector_norm(x)
+    y = torch.empty_like(x)
+    lam_prev = 0.0
+    for it in range(max_iter):
+        check(lib.hsd_laplacian_spmv(engine._ptr(csr.rowptr), engine._ptr(csr.col), n, engine._ptr(x),
+                                     engine._ptr(y), engine._stream()))
+        if it % 8 == 7:           # the Rayleigh quotient needs a host read: poll every 8 iterations
+            lam = float(torch.dot(x, y))
+            if abs(lam - lam_prev) <= tol * abs(lam):
+                lam_prev = lam
+                break
+            lam_prev = lam
+        nrm = torch.linalg.vector_norm(y)
+        x, y = y / nrm, x
+    return 1.01 * lam_prev
+
+
+def estimate_lmax_arpack(g: CSRGraph) -> float:
+    """The pygsp recipe itself (host ARPACK: k=1, tol=5e-3, ncv=min(N,10)) with a fixed-seed start
+    vector; kept for comparison, not used by the models."""
     import scipy.sparse as sp
     import scipy.sparse.linalg as spla
     n = g.n

@@ -215,6 +215,12 @@ int hsd_cheb_spmm(const int32_t* rowptr, const int32_t* col, int32_t n_nodes,
                   int32_t col0, int32_t n_cols, double threshold,
                   double* work, double* out, void* stream);
 
+/* y = L x, L = D - A from the CSR (unit weights, self-loops cancel), one FP64 vector.  The
+ * building block of the lmax estimate that replaces pygsp's Graph.estimate_lmax (ARPACK;
+ * call sites model/HSD.py:51, model/multiscale_HSD.py:28) with a power iteration on the device. */
+int hsd_laplacian_spmv(const int32_t* rowptr, const int32_t* col, int32_t n_nodes,
+                       const double* x, double* y, void* stream);
+
 /* ---- K5: ring gather-reduce for MultiHSD embeddings -------------------------
  * Replaces model/multiscale_HSD.py:45-61 (get_triple) / :64-73 (get_layer_sum):
  * emb[col0+c][s][h][0..1] = [sum, mean] of psiT[s][v][c] over v in ring_h(col0+c);

@@ -233,3 +233,19 @@ def test_graphwave_barbell_classes(golden_graphs):
         v = np.mean(np.exp(1j * x * t))
         ref += [v.real, v.imag]
     np.testing.assert_allclose(emb[nodes[3]], np.array(ref), rtol=1e-10, atol=1e-12)
+
+
+def test_device_lmax_estimate(golden_graphs):
+    """Power iteration on the device vs the dense eigenvalue and vs the pygsp/ARPACK recipe."""
+    from hsd_b200 import wavelets as wv
+    from hsd_b200.graph import CSRGraph, powerlaw_graph
+    for name in ["karate", "europe", "usa", "tree"]:
+        nodes = golden_graphs[f"{name}_nodes"]
+        g = CSRGraph.from_edges(len(nodes), golden_graphs[f"{name}_edges"])
+        adj = [g.neighbors(i).astype(np.int64) for i in range(g.n)]
+        exact = O.estimate_lmax(O.laplacian_dense(adj))          # 1.01 * dense lambda_max
+        got = wv.estimate_lmax(g)
+        assert abs(got - exact) <= 1e-4 * exact, (name, got, exact)
+        assert abs(wv.estimate_lmax_arpack(g) - exact) <= 1e-2 * exact
+    g = powerlaw_graph(20000, 5, seed=0)
+    assert abs(wv.estimate_lmax(g) - wv.estimate_lmax_arpack(g)) <= 5e-3 * wv.estimate_lmax(g)

@@ -1,11 +1,19 @@
 """Row-block sharding of the degree-mode path over the GPUs of one box.
 
 One process per GPU (torch.distributed, NCCL).  Every D[i, j] depends only on
-signature rows i and j, so rank r owns a contiguous block of rows: it runs the
-BFS + degree-CDF kernel for its own sources, contributes its slice of the
-signature table with ONE in-place all-gather (the only collective on the path;
-SURVEY.md §8 e), and computes its rows of D against all columns.  The result
-stays sharded on the devices.
+signature rows i and j (SURVEY.md §8 e).  The RESULT is row-block sharded: rank r
+owns rows [r*per, (r+1)*per).  The WORK is dealt differently so that it balances:
+
+* BFS sources are dealt round-robin (node s -> rank s % world; contiguous blocks
+  would give one rank all the hubs);
+* peer mode (default under bench.py): the signature table and the result blocks are
+  torch symmetric-memory allocations mapped into every rank over NVLink.  The BFS
+  kernel stores each signature row into all ranks' tables as it is produced (fused
+  all-gather), and the pairwise kernel computes each symmetric tile once in the whole
+  job and stores it, mirrored, into the owners' blocks.  No collective is issued;
+  two device-side barriers per step order the stores;
+* fallback (peer=False): ONE in-place NCCL all-gather of the signature table, then
+  every rank computes its rows against all columns (twice the arithmetic).
 
 The reference's counterpart is multiprocessing.Pool over rows with the whole
 model pickled per task (model/HSD.py:118-137).
@@ -155,7 +163,8 @@ class ShardedDegreeHSD:
         cur.wait_stream(self.side)
 
     def gather(self) -> None:
-        """The one collective: in-place all-gather of the signature table (NCCL over NVLink)."""
+        """Make every rank's signature table complete: a barrier in peer mode (the rows were
+        already stored by the BFS kernels), else the in-place NCCL all-gather."""
         if self.world == 1:
             return
         if self.sig_peer_ptrs is not None:

@@ -66,6 +66,8 @@ class HSD(object):
         self.empty = "raise"   # empty-ring policy in degree mode: 'raise' (scipy) | 'zero'
 
         self.csr = CSRGraph.from_networkx(graph)
+        # every edge list the reference ships is unweighted; the CSR kernels assume unit weights
+        self._weighted = any(d.get("weight", 1.0) != 1.0 for _, _, d in graph.edges(data=True))
         self._A = None
         self._L = None
         self._dg = None
@@ -154,6 +156,9 @@ class HSD(object):
     # ---- wavelets (model/HSD.py:48-67) ----
     def _wavelets_device(self, scale, approx=True) -> torch.Tensor:
         if approx:
+            if self._weighted:
+                raise NotImplementedError("the Chebyshev kernel takes unit edge weights; use approx=False "
+                                          "(dense eigh honours weights like the reference)")
             if self.lmax is None:
                 self.lmax = _wav.estimate_lmax(self.csr)
             return _wav.cheb_wavelets_dense(self._device_csr(), float(scale), self.lmax,

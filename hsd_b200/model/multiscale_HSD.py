@@ -63,6 +63,8 @@ class MultiHSD(HSD):
         sizes = rings.sizes.contiguous()
         thr = self.THRESHOLD_COEFF * 1.0 / n
         if approx:
+            if self._weighted:
+                raise NotImplementedError("the Chebyshev kernel takes unit edge weights; use approx=False")
             csr = self._device_csr()
             if self.lmax is None:
                 self.lmax = _wav.estimate_lmax(self.csr)

@@ -44,14 +44,13 @@ struct BfsArgs {
 };
 
 // `seen` = every node discovered so far (all earlier rings + the part of the current ring found
-// so far).  One plain read filters the common case; a new node costs two shared-memory atomics.
-__device__ __forceinline__ void visit_neighbor(int u, uint32_t* __restrict__ seen,
-                                               uint32_t* __restrict__ ring) {
+// so far).  One plain read filters the common case; a new node costs ONE fire-and-forget
+// shared-memory atomic.  The ring itself is recovered after the level as seen & ~snapshot, where
+// the snapshot of `seen` taken at the start of the level sits in the ring buffer.
+__device__ __forceinline__ void visit_neighbor(int u, uint32_t* __restrict__ seen) {
     const uint32_t m = 1u << (u & 31);
     const int w = u >> 5;
-    if (!(*((volatile uint32_t*)&seen[w]) & m)) {
-        if (!(atomicOr(&seen[w], m) & m)) atomicOr(&ring[w], m);
-    }
+    if (!(*((volatile uint32_t*)&seen[w]) & m)) atomicOr(&seen[w], m);
 }
 
 // One CTA per source.  Shared memory: the `seen` bitmap, two ring bitmaps (ping-pong), the prefix
@@ -115,7 +114,7 @@ bfs_ring_signature_kernel(const BfsArgs p) {
     for (int h = 1; h <= p.hops; ++h) {
         uint32_t* F = (h & 1) ? R0 : R1;    // ring h-1 (prefix popcounts in P)
         uint32_t* Fn = (h & 1) ? R1 : R0;   // ring h
-        for (int w = tid; w < nw; w += THREADS) Fn[w] = 0u;
+        for (int w = tid; w < nw; w += THREADS) Fn[w] = S[w];   // snapshot of `seen` before this level
         __syncthreads();
 
         for (int r0 = 0; r0 < n_cur; r0 += FL_CAP) {
@@ -177,10 +176,10 @@ bfs_ring_signature_kernel(const BfsArgs p) {
                     // aligned 16-byte groups; entries outside [i, i_end) are masked
                     for (int g = i & ~3; g < i_end; g += 4) {
                         const int4 c = __ldg(reinterpret_cast<const int4*>(p.col + g));
-                        if (g >= i && g < i_end) visit_neighbor(c.x, S, Fn);
-                        if (g + 1 >= i && g + 1 < i_end) visit_neighbor(c.y, S, Fn);
-                        if (g + 2 >= i && g + 2 < i_end) visit_neighbor(c.z, S, Fn);
-                        if (g + 3 >= i && g + 3 < i_end) visit_neighbor(c.w, S, Fn);
+                        if (g >= i && g < i_end) visit_neighbor(c.x, S);
+                        if (g + 1 >= i && g + 1 < i_end) visit_neighbor(c.y, S);
+                        if (g + 2 >= i && g + 2 < i_end) visit_neighbor(c.z, S);
+                        if (g + 3 >= i && g + 3 < i_end) visit_neighbor(c.w, S);
                     }
                     e = k_end;
                     ++k;
@@ -189,10 +188,14 @@ bfs_ring_signature_kernel(const BfsArgs p) {
             __syncthreads();
         }
 
-        // ---- ring h = Fn: prefix popcount into P ----
+        // ---- ring h = seen & ~snapshot (into Fn); prefix popcount into P ----
         const int w_lo = min(tid * cpt, nw), w_hi = min(w_lo + cpt, nw);
         int local = 0;
-        for (int w = w_lo; w < w_hi; ++w) local += __popc(Fn[w]);
+        for (int w = w_lo; w < w_hi; ++w) {
+            const uint32_t r = S[w] & ~Fn[w];
+            Fn[w] = r;
+            local += __popc(r);
+        }
         int n_ring;
         int run = block_exclusive_scan<THREADS>(local, warp_tot, &n_ring);
         for (int w = w_lo; w < w_hi; ++w) {

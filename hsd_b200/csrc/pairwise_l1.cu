@@ -261,6 +261,142 @@ pairwise_l1_kernel(const __grid_constant__ CUtensorMap tmap, const PairArgs p) {
     }
 }
 
+// ---- 128 x 64 tile variant -------------------------------------------------------------------
+// Same pipeline with a 64-column B tile: 8 x 4 register tiles (32 accumulators) fit 3 CTAs per SM
+// (24 warps instead of 16) and halve the tile granularity, which is what matters when a launch has
+// only a few tiles per CTA slot (an 8-GPU run of the 20k-node graph: 5.2 waves of 128 x 128 tiles).
+// Symmetric mode: tile row I (128 rows) owns column tiles J = 2I .. tiles_c-1 (64 columns each);
+// J in {2I, 2I+1} together cover the diagonal 128 x 128 block in full, J >= 2I+2 is mirrored.
+constexpr int TILE_N64 = 64;
+constexpr uint32_t STAGE_BYTES_N64 = (uint32_t)KC * (TILE + TILE_N64) * sizeof(float);
+
+struct __align__(128) PairSmemN64 {
+    float a[STAGES][KC][TILE];
+    float b[STAGES][KC][TILE_N64];
+    unsigned long long full[STAGES];
+    unsigned long long empty[STAGES];
+};
+
+// tile row i starts at first(i) = i * (tiles_c + 1 - i)
+__device__ __forceinline__ void tri_decode_n64(int t, int tiles_r, int tiles_c, int& I, int& J) {
+    const float b = (float)tiles_c + 1.f;
+    int i = (int)((b - sqrtf(fmaxf(b * b - 4.f * (float)t, 0.f))) * 0.5f);
+    i = max(0, min(i, tiles_r - 1));
+    while (i > 0 && i * (tiles_c + 1 - i) > t) --i;
+    while (i + 1 < tiles_r && (i + 1) * (tiles_c - i) <= t) ++i;
+    I = i;
+    J = 2 * i + (t - i * (tiles_c + 1 - i));
+}
+
+__global__ void __launch_bounds__(PAIR_THREADS, 3)
+pairwise_l1_n64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                       const PairArgs p) {
+    extern __shared__ __align__(128) unsigned char pair_smem_raw[];
+    PairSmemN64& sm = *reinterpret_cast<PairSmemN64*>(pair_smem_raw);
+
+    int I, J;
+    if (p.symmetric) {
+        tri_decode_n64(blockIdx.x * p.tile_stride + p.tile_offset, p.tiles_r, p.tiles_c, I, J);
+    } else {
+        I = blockIdx.x / p.tiles_c;
+        J = blockIdx.x - I * p.tiles_c;
+    }
+    const int i_base = p.row0 + I * TILE;
+    const int j_base = p.col0 + J * TILE_N64;
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(smem_u32(&sm.full[s]), 1);
+            mbar_init(smem_u32(&sm.empty[s]), PAIR_THREADS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue_chunk = [&](int n) {
+        const int s = n % STAGES;
+        const uint32_t ph = (n / STAGES) & 1;
+        mbar_wait(smem_u32(&sm.empty[s]), ph ^ 1u);
+        const uint32_t full = smem_u32(&sm.full[s]);
+        mbar_expect_tx(full, STAGE_BYTES_N64);
+        tma_load_2d(smem_u32(&sm.a[s][0][0]), &tmap_a, i_base, n * KC, full);
+        tma_load_2d(smem_u32(&sm.b[s][0][0]), &tmap_b, j_base, n * KC, full);
+    };
+    if (tid == 0)
+        for (int n = 0; n < LOOKAHEAD && n < p.k_chunks; ++n) issue_chunk(n);
+
+    const int tx = tid & 15, ty = tid >> 4;
+    float acc[8][4];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+
+    uint32_t ready = 0;
+    for (int c = 0; c < p.k_chunks; ++c) {
+        if (tid == 0 && c + LOOKAHEAD < p.k_chunks) issue_chunk(c + LOOKAHEAD);
+        const int s = c % STAGES;
+        const uint32_t ph = (c / STAGES) & 1;
+        if (!ready) mbar_wait(smem_u32(&sm.full[s]), ph);
+        ready = (c + 1 < p.k_chunks)
+                    ? mbar_test(smem_u32(&sm.full[(c + 1) % STAGES]), ((c + 1) / STAGES) & 1) : 0u;
+#pragma unroll
+        for (int kk = 0; kk < KC; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&sm.a[s][kk][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&sm.a[s][kk][64 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&sm.b[s][kk][tx * 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[4] = {b0.x, b0.y, b0.z, b0.w};
+            float d[8][4];
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) d[r][q] = av[r] - bv[q];
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[r][q] += fabsf(d[r][q]);
+        }
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(smem_u32(&sm.empty[s]));
+    }
+
+    const int row_end = p.row0 + p.n_rows, col_end = p.col0 + p.n_cols;
+    const bool mirror = p.symmetric && (J >= 2 * I + 2);
+    const bool full_tile = (i_base + TILE <= row_end) && (j_base + TILE_N64 <= col_end) && p.vec_ok;
+    if (full_tile) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int i = i_base + (r < 4 ? ty * 4 + r : 64 + ty * 4 + (r - 4));
+            *reinterpret_cast<float4*>(row_ptr(p, i) + j_base + tx * 4) =
+                make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+        }
+        if (mirror) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float* o = row_ptr(p, j_base + tx * 4 + q) + i_base;
+                *reinterpret_cast<float4*>(o + ty * 4) = make_float4(acc[0][q], acc[1][q], acc[2][q], acc[3][q]);
+                *reinterpret_cast<float4*>(o + 64 + ty * 4) = make_float4(acc[4][q], acc[5][q], acc[6][q], acc[7][q]);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int i = i_base + (r < 4 ? ty * 4 + r : 64 + ty * 4 + (r - 4));
+            if (i >= row_end) continue;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int j = j_base + tx * 4 + q;
+                if (j >= col_end) continue;
+                row_ptr(p, i)[j] = acc[r][q];
+                if (mirror) row_ptr(p, j)[i] = acc[r][q];
+            }
+        }
+    }
+}
+
 // ---- FP32 issue-peak probe: same instruction mix as the inner loop, no memory ----
 __global__ void __launch_bounds__(256, 2) fp32_peak_probe_kernel(float* sink, int iters) {
     float a[8], b[8], acc[8][8];
@@ -331,6 +467,37 @@ static int launch_pairwise(const float* sigT, int32_t k_used, int64_t n_pad, Pai
     a.k_chunks = k_pad / KC;
     HSD_REQUIRE(n_tiles < (1ll << 31), "too many tiles for one launch");
     if (n_tiles <= 0) return HSD_OK;
+
+    static int tile_n = -1;   // HSD_PAIR_TILE_N=64 / 128 forces a variant; default: by tiles per CTA slot
+    if (tile_n < 0) { const char* e = getenv("HSD_PAIR_TILE_N"); tile_n = e ? atoi(e) : 0; }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const bool use_n64 = tile_n == 64 || (tile_n == 0 && n_tiles < (long long)sms * 2 * 8);
+    if (use_n64) {
+        // re-derive the tile grid for 64-column tiles
+        const int tr = a.tiles_r;
+        const int tc = (a.n_cols + TILE_N64 - 1) / TILE_N64;
+        const long long total = a.symmetric ? (long long)tr * tc - (long long)tr * (tr - 1) : (long long)tr * tc;
+        const long long mine = total > a.tile_offset ? (total - a.tile_offset + a.tile_stride - 1) / a.tile_stride : 0;
+        if (mine <= 0) return HSD_OK;
+        HSD_REQUIRE(mine < (1ll << 31), "too many tiles for one launch");
+        a.tiles_c = tc;
+        CUtensorMap tmap_b;
+        const cuuint32_t box_b[2] = {(cuuint32_t)TILE_N64, (cuuint32_t)KC};
+        cr = encode(&tmap_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(sigT), gdim, gstride, box_b,
+                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) {
+            set_error("cuTensorMapEncodeTiled (B tile) failed with CUresult %d", (int)cr);
+            return HSD_ERR_CUDA;
+        }
+        const int smem64 = (int)sizeof(PairSmemN64);
+        HSD_CUDA_TRY(cudaFuncSetAttribute(pairwise_l1_n64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem64));
+        pairwise_l1_n64_kernel<<<(unsigned)mine, PAIR_THREADS, smem64, stream>>>(tmap, tmap_b, a);
+        HSD_CUDA_TRY(cudaGetLastError());
+        return HSD_OK;
+    }
 
     const int smem = (int)sizeof(PairSmem);
     static int unroll = 0;   // tuning knob, read once: HSD_PAIR_UNROLL in {4, 8, 16}

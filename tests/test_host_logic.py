@@ -174,3 +174,22 @@ def test_rw_formats_round_trip(tmp_path, robust_csv):
     assert np.array_equal(rw.read_distance(str(q), 3), D)
     with pytest.raises(FileNotFoundError):
         rw.read_vectors(str(tmp_path / "missing.csv"))
+
+
+def test_reference_side_modules_stay_importable_through_the_shim():
+    """With $HSD_REFERENCE_ROOT set, `from tools import evaluate, dataloader` (main.py:7 of the
+    reference) resolves to the reference's own files while tools.hierarchy / tools.rw stay ours."""
+    import subprocess
+    import sys
+    ref = "/root/reference"
+    if not os.path.isdir(os.path.join(ref, "tools")):
+        pytest.skip("reference checkout not present (GPU box)")
+    code = ("import tools; from tools import evaluate, dataloader, rw, util, hierarchy; "
+            "import model; "
+            "print(evaluate.__file__); print(hierarchy.__name__); print(rw.__name__); print(model.HSD.__module__)")
+    env = dict(os.environ, HSD_REFERENCE_ROOT=ref, PYTHONPATH=ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=ROOT, timeout=300)
+    assert out.returncode == 0, out.stderr[-1500:]
+    lines = out.stdout.strip().splitlines()
+    assert lines[0].startswith(ref) and lines[1] == "hsd_b200.tools.hierarchy"
+    assert lines[2] == "hsd_b200.tools.rw" and lines[3] == "hsd_b200.model.HSD"

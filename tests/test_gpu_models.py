@@ -249,3 +249,37 @@ def test_device_lmax_estimate(golden_graphs):
         assert abs(wv.estimate_lmax_arpack(g) - exact) <= 1e-2 * exact
     g = powerlaw_graph(20000, 5, seed=0)
     assert abs(wv.estimate_lmax(g) - wv.estimate_lmax_arpack(g)) <= 5e-3 * wv.estimate_lmax(g)
+
+
+def test_reference_main_py_flow(golden_graphs):
+    """The call sequence of the reference's main.py:9-34 (base_HSD_Test) and :36-53
+    (multi_HSD_Test) against the drop-in classes, including the drift names its callers use
+    (construct_hierarchy, laplacian, eigenvalues / eigenvectors, wavelets)."""
+    from model import HSD, MultiHSD
+    from tools import util
+    g = nx_graph(golden_graphs, "europe")
+    model = HSD(g, "europe", 0, 3, "wasserstein")
+    model.construct_hierarchy()
+    model.eigenvalues, model.eigenvectors = np.linalg.eigh(model.laplacian)
+    scale_min, scale_max = util.recommend_scale_range(list(model.eigenvalues))
+    assert 0 < scale_min < scale_max
+    for scale in np.linspace(scale_min, scale_max, num=2):
+        model.scale = scale
+        model.calculate_wavelets(model.scale, approx=True)
+        dists = model.parallel_calculate_HSD(n_workers=10)
+        assert dists.shape == (model.n_node, model.n_node) and np.allclose(dists, dists.T)
+        assert np.all(np.diag(dists) == 0) and np.isfinite(dists).all() and dists.max() > 0
+        assert model.distMat is dists
+    # exact path with the caller-assigned eigen-decomposition equals the internal one
+    W1 = model.calculate_wavelets(0.5, approx=False)
+    model.eigenvalues = model.eigenvectors = None
+    W2 = model.calculate_wavelets(0.5, approx=False)
+    np.testing.assert_allclose(W1, W2, rtol=1e-8, atol=1e-4 / model.n_node * 1.000001)
+
+    m2 = MultiHSD(g, "europe", 3, 5)
+    m2.init()
+    emb = m2.parallel_embed(n_workers=10)
+    assert set(emb.keys()) == set(m2.nodes) and len(emb[m2.nodes[0]]) == 5 * 4 * 2
+    assert m2.embeddings is emb
+    nodes0 = m2.hierarchy[m2.nodes[0]]
+    assert nodes0[0] == [m2.nodes[0]] and len(nodes0) == 4

@@ -92,3 +92,36 @@ def test_c2_paths_agree_bitwise(c2):
     torch.cuda.synchronize()
     got = torch.cat([b[:, :n] for b in blocks], 0)[:n]
     assert torch.equal(got, D)
+
+
+def test_c3_sampled_pairs_match_oracle():
+    """The north-star target size (BA 100 000 nodes, 4 hops; SURVEY C3: B = 248, K = 989): three
+    rows of the device result against scipy W1 over the reference's BFS rings on sampled columns,
+    plus the structural properties, without materialising more than the row block needed."""
+    import torch
+    from hsd_b200 import engine
+    from hsd_b200.graph import powerlaw_graph
+    g = powerlaw_graph(100000, 5, seed=0)
+    dg = engine.DeviceGraph.upload(g)
+    assert dg.n_bins == 248 and dg.k_used(4) == 989
+    sig, sizes, _, status = engine.ring_signature_degree(dg, 4)
+    assert int(status.item()) == 0
+    k = dg.k_used(4)
+    sigT = engine.alloc_signature_table(k, g.n, sig.device)
+    engine.signature_transpose(sig, k, sigT)
+    # rows 0..127 (one tile row, includes the biggest hubs) and the last 128 rows, against all columns
+    top = engine.pairwise_l1(sigT, g.n, 0, 128, 0, g.n, symmetric=False, k_used=k)
+    bot = engine.pairwise_l1(sigT, g.n, g.n - 128, 128, 0, g.n, symmetric=False, k_used=k)
+    torch.cuda.synchronize()
+    assert torch.equal(top[:, g.n - 128:], bot[:, :128].t())            # symmetry across the two blocks
+    assert torch.all(torch.diagonal(top[:, :128]) == 0)
+    rng = np.random.default_rng(2)
+    cols = sorted(set(rng.integers(0, g.n, size=40).tolist()) | {0, 1, 99999})
+    rows = [0, 5, 99999]
+    adj = [g.neighbors(i).astype(np.int64) for i in range(g.n)]
+    ref = O.degree_distance_rows(adj, 4, rows, cols)
+    got = np.stack([top[0].cpu().numpy()[cols], top[5].cpu().numpy()[cols], bot[127].cpu().numpy()[cols]]).astype(np.float64)
+    np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-6 * ref.max())
+    rings = O.all_rings(adj, 4, rows)
+    for r in rows:
+        assert sizes[r].tolist() == [len(l) for l in rings[r]]

@@ -115,3 +115,14 @@ if "c5h2" in which:
         t0 = time.perf_counter(); D = m.structural_distance_update(); torch.cuda.synchronize(); t_inc = time.perf_counter() - t0
         print(json.dumps({"config": "C5 variant hop=2", "n": n, "hop": hop, "inserted_edges": k_ins,
                           "affected_rows": int(m.last_affected.numel()), "full_s": t_full, "incremental_s": t_inc}))
+
+if "topk" in which:
+    for n, hops in [(20000, 3), (100000, 4)]:
+        g = powerlaw_graph(n, 5, seed=0); dg = engine.DeviceGraph.upload(g)
+        D, _ = engine.degree_distance_device(dg, hops)
+        t, (idx, val) = timed(lambda: engine.topk_rows(D, 20))
+        byts = 4.0 * n * n
+        print(json.dumps({"config": "k-NN top-20 on the resident matrix", "n": n, "ms": t, "matrix_GB": byts / 1e9,
+                          "matrix_reads_GBs": byts / (t * 1e-3) / 1e9, "hbm_peak": peaks["hbm_gbs"],
+                          "d2h_bytes_instead_of_matrix": int(idx.numel() * 8)}))
+        del D

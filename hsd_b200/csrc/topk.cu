@@ -64,29 +64,47 @@ topk_rows_kernel(const float* __restrict__ D, int64_t ld, int n_cols, int k, int
     const int need_ties = sel_need;            // how many elements equal to it belong to the result
     if (tid == 0) { n_less = 0; n_tie = 0; }
     __syncthreads();
-    // ---- collect: strictly smaller in any order, ties in ascending column order ----
-    for (int base = 0; base < n_cols; base += TK_THREADS) {
-        const int j = base + tid;
-        bool ok = j < n_cols && j != self_col && tk_allowed(mask, j);
-        const uint32_t u = ok ? __float_as_uint(d[j]) : 0xffffffffu;
-        if (ok && u < kth) {
+    // ---- collect: strictly smaller in any order; ties in ascending column order ----
+    // Fast path: when exactly `need_ties` elements equal the k-th value they all belong to the
+    // result and their order does not matter (the final sort fixes it).  Only when there are more
+    // ties than needed does the block fall back to the ordered placement (a scan per 256 columns).
+    for (int j = tid; j < n_cols; j += TK_THREADS) {
+        if (j == self_col || !tk_allowed(mask, j)) continue;
+        const uint32_t u = __float_as_uint(d[j]);
+        if (u < kth) {
             const int p = atomicAdd(&n_less, 1);
             res_v[p] = __uint_as_float(u);
             res_i[p] = j;
+        } else if (u == kth) {
+            const int t = atomicAdd(&n_tie, 1);
+            if (t < need_ties) {                       // tentative: valid iff n_tie ends == need_ties
+                res_v[(k - need_ties) + t] = __uint_as_float(u);
+                res_i[(k - need_ties) + t] = j;
+            }
         }
-        // ordered tie placement: exclusive scan of the tie flags across the block
-        const int is_tie = (ok && u == kth) ? 1 : 0;
-        int total;
-        const int before = block_exclusive_scan<TK_THREADS>(is_tie, warp_tot, &total);
-        const int t0 = n_tie;                  // read before anyone updates it (scan synced)
+    }
+    __syncthreads();
+    if (n_tie > need_ties) {                            // uniform across the block
         __syncthreads();
-        if (is_tie && t0 + before < need_ties) {
-            const int p = (k - need_ties) + t0 + before;
-            res_v[p] = __uint_as_float(u);
-            res_i[p] = j;
+        if (tid == 0) n_tie = 0;
+        __syncthreads();
+        for (int base = 0; base < n_cols; base += TK_THREADS) {
+            const int j = base + tid;
+            const bool ok = j < n_cols && j != self_col && tk_allowed(mask, j);
+            const int is_tie = (ok && __float_as_uint(d[j]) == kth) ? 1 : 0;
+            int total;
+            const int before = block_exclusive_scan<TK_THREADS>(is_tie, warp_tot, &total);
+            const int t0 = n_tie;                       // read before anyone updates it (scan synced)
+            __syncthreads();
+            if (is_tie && t0 + before < need_ties) {
+                const int p = (k - need_ties) + t0 + before;
+                res_v[p] = __uint_as_float(kth);
+                res_i[p] = j;
+            }
+            if (tid == 0) n_tie = t0 + total;
+            __syncthreads();
+            if (t0 + total >= need_ties) break;         // uniform: every needed tie is placed
         }
-        if (tid == 0) n_tie = t0 + total;
-        __syncthreads();
     }
     // ---- sort the k results by (distance, column): bitonic over 64 slots ----
     const int avail = min(k, n_less + min(n_tie, need_ties));

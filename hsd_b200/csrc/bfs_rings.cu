@@ -12,9 +12,21 @@
 // atomics (the skewed degree distribution would serialise them).  The same prefix popcount gives
 // every ring member its slot in a compact frontier list, which is expanded edge-balanced.
 #include <stdlib.h>
+#include <algorithm>
 #include "hsd_common.cuh"
 
 namespace hsd {
+
+// size (uint32 words) of the global bitmap workspace registered with hsd_bfs_set_workspace
+static thread_local long long g_ws_words = 0;
+static thread_local uint32_t* g_ws = nullptr;
+
+// test knob: HSD_BFS_FORCE_GLOBAL=1 sends every graph through the global-workspace variant
+static bool force_global() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("HSD_BFS_FORCE_GLOBAL"); v = (e && atoi(e)) ? 1 : 0; }
+    return v == 1;
+}
 
 constexpr int FL_CAP = 2048;                       // frontier nodes expanded per round
 
@@ -41,6 +53,7 @@ struct BfsArgs {
     int32_t empty_as_zero;
     int32_t* status;
     int32_t cta_threads;   // 0 = choose from the graph size
+    uint32_t* ws;          // global bitmap workspace (only for graphs too large for shared memory)
 };
 
 // `seen` = every node discovered so far (all earlier rings + the part of the current ring found
@@ -64,25 +77,15 @@ __device__ __forceinline__ void visit_neighbor(int u, uint32_t* __restrict__ see
 // stall samples on that barrier); scalar 4-byte loads relied on L1 keeping each 32-byte sector
 // alive across 8 iterations and re-fetched it 4x from L2 instead (59 % L1 hit rate).
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS)
-bfs_ring_signature_kernel(const BfsArgs p) {
+__device__ __forceinline__ void bfs_one_source(const BfsArgs& p, const int sidx, uint32_t* __restrict__ S,
+                                               uint32_t* __restrict__ R0, uint32_t* __restrict__ R1,
+                                               uint32_t* __restrict__ P, int* warp_tot, int* fl_start,
+                                               int* fl_eo) {
     constexpr int FL_PER_THREAD = FL_CAP / THREADS;
-    extern __shared__ uint32_t bfs_smem[];
-    __shared__ int warp_tot[THREADS / 32];
-    __shared__ int fl_start[FL_CAP];
-    __shared__ int fl_eo[FL_CAP + 1];
-
     const int nw = p.n_words;
-    uint32_t* S = bfs_smem;
-    uint32_t* R0 = S + nw;
-    uint32_t* R1 = R0 + nw;
-    uint32_t* P = R1 + nw;
     const int tid = threadIdx.x;
     const int hops1 = p.hops + 1;
     const int nb1 = p.n_bins - 1;
-
-    const int sidx = blockIdx.x;
-    if (sidx >= p.n_src) return;
     const int s = p.src_nodes[sidx];
     const int64_t row = p.out_rows[sidx];
 
@@ -238,38 +241,73 @@ bfs_ring_signature_kernel(const BfsArgs p) {
     }
 }
 
-static int launch_bfs(const BfsArgs& a, cudaStream_t stream) {
+// One CTA per source (bitmaps in shared memory), or — GLOBAL_BM, graphs whose four bitmaps exceed
+// shared memory — persistent CTAs that keep their bitmaps in an L2-resident slice of a
+// caller-provided global workspace and walk several sources each.
+//
+// MINB (min CTAs per SM for __launch_bounds__; 0 = unspecified): left to itself ptxas targets full
+// occupancy (32 registers at 512 threads, with a 16-byte spill); the global variant runs 2 CTAs per
+// SM and gets the 56 registers it wants.  (A 40-register, spill-free build of the 512-thread
+// shared-memory variant measured the same 44.9 ms at C3, so that one is left alone.)
+template <int THREADS, bool GLOBAL_BM, int MINB = 0>
+__global__ void __launch_bounds__(THREADS, MINB)
+bfs_ring_signature_kernel(const BfsArgs p) {
+    extern __shared__ uint32_t bfs_smem[];
+    __shared__ int warp_tot[THREADS / 32];
+    __shared__ int fl_start[FL_CAP];
+    __shared__ int fl_eo[FL_CAP + 1];
+    const int nw = p.n_words;
+    if (!GLOBAL_BM) {
+        if ((int)blockIdx.x >= p.n_src) return;
+        bfs_one_source<THREADS>(p, blockIdx.x, bfs_smem, bfs_smem + nw, bfs_smem + 2 * nw, bfs_smem + 3 * nw,
+                                warp_tot, fl_start, fl_eo);
+    } else {
+        uint32_t* base = p.ws + (size_t)blockIdx.x * 4 * nw;
+        for (int sidx = blockIdx.x; sidx < p.n_src; sidx += gridDim.x) {
+            bfs_one_source<THREADS>(p, sidx, base, base + nw, base + 2 * nw, base + 3 * nw, warp_tot, fl_start, fl_eo);
+            __syncthreads();   // the next source re-initialises the bitmaps
+        }
+    }
+}
+
+static int launch_bfs(const BfsArgs& a_in, cudaStream_t stream) {
+    BfsArgs a = a_in;
     if (a.n_src == 0) return HSD_OK;
     const size_t smem = (size_t)4 * a.n_words * sizeof(uint32_t);
-    if (smem > 200 * 1024) {
-        set_error("hsd_bfs: %d nodes need %zu B of bitmap shared memory (> 200 KB); "
-                  "graphs above ~400k nodes are not supported by this kernel", a.n_nodes, smem);
-        return HSD_ERR_UNSUPPORTED;
+    if (smem > 200 * 1024 || force_global()) {
+        // bitmaps do not fit shared memory (> ~400k nodes): global workspace, persistent CTAs
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int grid = std::min<long long>(a.n_src, (long long)sms * 2);
+        const long long need = (long long)grid * 4 * a.n_words;
+        if (!a.ws || need > g_ws_words) {
+            set_error("hsd_bfs: %d nodes need a global bitmap workspace of %lld uint32 words "
+                      "(hsd_bfs_workspace_words); got %lld", a.n_nodes, need, a.ws ? g_ws_words : 0ll);
+            return HSD_ERR_UNSUPPORTED;
+        }
+        bfs_ring_signature_kernel<512, true, 2><<<grid, 512, 0, stream>>>(a);
+        HSD_CUDA_TRY(cudaGetLastError());
+        return HSD_OK;
     }
+    a.ws = nullptr;
     // large graphs: the bitmaps limit an SM to a few CTAs, so use 512-thread CTAs to keep warps resident;
     // small graphs: per-level fixed costs (barriers, scans) dominate, so use small CTAs and more of them
-    static int force = -1;   // tuning knob: HSD_BFS_THREADS in {128, 256, 512}
+    static int force = -1;   // tuning knob: HSD_BFS_THREADS in {128, 256, 512, 1024}
     if (force < 0) { const char* e = getenv("HSD_BFS_THREADS"); force = e ? atoi(e) : 0; }
     const int threads = a.cta_threads ? a.cta_threads : (force ? force : (a.n_nodes > 48 * 1024 ? 512 : 256));
-    if (threads == 128) {
-        HSD_CUDA_TRY(cudaFuncSetAttribute(bfs_ring_signature_kernel<128>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        bfs_ring_signature_kernel<128><<<a.n_src, 128, smem, stream>>>(a);
-    } else if (threads == 1024) {
-        HSD_CUDA_TRY(cudaFuncSetAttribute(bfs_ring_signature_kernel<1024>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        bfs_ring_signature_kernel<1024><<<a.n_src, 1024, smem, stream>>>(a);
-    } else if (threads == 512) {
-        HSD_CUDA_TRY(cudaFuncSetAttribute(bfs_ring_signature_kernel<512>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        bfs_ring_signature_kernel<512><<<a.n_src, 512, smem, stream>>>(a);
-    } else {
-        HSD_CUDA_TRY(cudaFuncSetAttribute(bfs_ring_signature_kernel<256>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        bfs_ring_signature_kernel<256><<<a.n_src, 256, smem, stream>>>(a);
+    auto launch = [&](auto kern, int t) -> int {
+        HSD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<a.n_src, t, smem, stream>>>(a);
+        HSD_CUDA_TRY(cudaGetLastError());
+        return HSD_OK;
+    };
+    switch (threads) {
+        case 128: return launch(bfs_ring_signature_kernel<128, false>, 128);
+        case 512: return launch(bfs_ring_signature_kernel<512, false>, 512);
+        case 1024: return launch(bfs_ring_signature_kernel<1024, false>, 1024);
+        default: return launch(bfs_ring_signature_kernel<256, false>, 256);
     }
-    HSD_CUDA_TRY(cudaGetLastError());
-    return HSD_OK;
 }
 
 }  // namespace hsd
@@ -295,7 +333,7 @@ static int ring_signature_degree_impl(float* const* sig_peers, int32_t n_peers,
     a.src_nodes = src_nodes; a.out_rows = out_rows; a.n_src = n_src; a.hops = hops;
     a.bin_end = bin_end; a.delta = delta; a.n_bins = sig ? n_bins : 1;
     a.sig = sig; a.sig_ld = sig_ld; a.sig_peers = sig_peers; a.n_peers = n_peers; a.ring_sizes = ring_sizes; a.ring_bitmaps = ring_bitmaps;
-    a.empty_as_zero = empty_as_zero; a.status = status; a.cta_threads = cta_threads;
+    a.empty_as_zero = empty_as_zero; a.status = status; a.cta_threads = cta_threads; a.ws = hsd::g_ws;
     return hsd::launch_bfs(a, (cudaStream_t)stream);
 }
 
@@ -332,4 +370,19 @@ extern "C" int hsd_bfs_rings(const int32_t* rowptr, const int32_t* col, int32_t 
     return hsd_ring_signature_degree(rowptr, col, n_nodes, src_nodes, out_rows, n_src, hops,
                                      nullptr, nullptr, 1, nullptr, 0, ring_sizes,
                                      ring_bitmaps, 1, nullptr, 0, stream);
+}
+
+// Graphs whose four N-bit bitmaps exceed shared memory (> ~400k nodes) need a global workspace.
+extern "C" int64_t hsd_bfs_workspace_words(int32_t n_nodes) {
+    const long long nw = ((long long)n_nodes + 31) / 32;
+    if (4 * nw * (long long)sizeof(uint32_t) <= 200 * 1024 && !hsd::force_global()) return 0;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return (long long)sms * 2 * 4 * nw;
+}
+
+extern "C" int hsd_bfs_set_workspace(uint32_t* workspace, int64_t words) {
+    hsd::g_ws = workspace;
+    hsd::g_ws_words = workspace ? words : 0;
+    return HSD_OK;
 }

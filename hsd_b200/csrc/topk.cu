@@ -3,10 +3,21 @@
 // ndarray to sklearn (tools/evaluate.py:61-69 via main.py:29); at N = 100k that is 40 GB, so the
 // selection runs where the matrix lives and only N x k pairs leave the GPU.
 //
-// One CTA per row: exact radix select on the float bit pattern (distances are >= 0, so the
-// unsigned order equals the numeric order) — three histogram passes (11 + 11 + 10 bits) find the
+// One CTA per row, two reads of the row (the second one an L2 hit):
+//   pass 1  every thread keeps the minimum of the elements it streams (16-byte loads, no atomics);
+//           the k-th smallest of those THREADS minima is an upper bound T of the row's k-th smallest
+//           value (the minima are distinct elements of the row), and a tight one: the row's k
+//           smallest elements mostly sit in different threads, so about k + k^2/THREADS elements are <= T;
+//   pass 2  everything <= T goes to a shared candidate list (one rarely-taken shared atomic each);
+//   sort    the candidates by (distance, column) — a single warp when there are <= 64 — and the
+//           first k are the answer, ties at the k-th value resolved by ascending column.
+// A row with more than TK_CAND candidates (a large class of nodes at exactly the same distance)
+// takes the exact radix select instead: three histogram passes over the float bit pattern
+// (11 + 11 + 10 bits; distances are >= 0, so the unsigned order equals the numeric order) find the
 // k-th smallest value, a fourth pass collects everything below it plus ties in ascending column
-// order, and a small bitonic sort orders the k results by (distance, column).
+// order.  That path alone measured 4.1 ms at N = 20k (shared-atomic contention on the few exponent
+// buckets the distances share); HSD_TOPK_RADIX=1 forces it (tests).
+#include <stdlib.h>
 #include "hsd_common.cuh"
 
 namespace hsd {
@@ -18,10 +29,10 @@ __device__ __forceinline__ bool tk_allowed(const uint32_t* __restrict__ mask, in
     return !mask || ((mask[j >> 5] >> (j & 31)) & 1u);
 }
 
-__global__ void __launch_bounds__(TK_THREADS)
-topk_rows_kernel(const float* __restrict__ D, int64_t ld, int n_cols, int k, int self_col0,
-                 const uint32_t* __restrict__ mask, int32_t* __restrict__ idx_out,
-                 float* __restrict__ val_out) {
+__device__ __noinline__ void
+topk_row_radix(const float* __restrict__ D, int64_t ld, int n_cols, int k, int self_col0,
+               const uint32_t* __restrict__ mask, int32_t* __restrict__ idx_out,
+               float* __restrict__ val_out) {
     __shared__ int hist[2048];
     __shared__ uint32_t sel_prefix, sel_mask;
     __shared__ int sel_need, n_less, n_tie;
@@ -131,6 +142,163 @@ topk_rows_kernel(const float* __restrict__ D, int64_t ld, int n_cols, int k, int
     }
 }
 
+__global__ void __launch_bounds__(TK_THREADS)
+topk_rows_radix_kernel(const float* __restrict__ D, int64_t ld, int n_cols, int k, int self_col0,
+                       const uint32_t* __restrict__ mask, int32_t* __restrict__ idx_out,
+                       float* __restrict__ val_out) {
+    topk_row_radix(D, ld, n_cols, k, self_col0, mask, idx_out, val_out);
+}
+
+constexpr int TK_CAND = 1024;   // candidate capacity of the two-pass kernel
+
+// (distance, column) "a sorts after b"
+__device__ __forceinline__ bool tk_after(float a, int ia, float b, int ib) {
+    return (a > b) || (a == b && ia > ib);
+}
+
+// Streams the row once: f(value, column) for every admissible column.  VEC4: 16-byte loads (row
+// start 16-byte aligned); the 4 mask bits of a group sit in one bitmap word.
+template <bool VEC4, typename F>
+__device__ __forceinline__ void tk_stream_row(const float* __restrict__ d, int n_cols, int self_col,
+                                              const uint32_t* __restrict__ mask, F f) {
+    const int tid = threadIdx.x;
+    if (VEC4) {
+        const int n4 = n_cols >> 2;
+        const float4* d4 = reinterpret_cast<const float4*>(d);
+#pragma unroll 4
+        for (int g = tid; g < n4; g += TK_THREADS) {
+            const float4 v = __ldg(d4 + g);
+            const int j = g << 2;
+            uint32_t ok = mask ? ((__ldg(mask + (j >> 5)) >> (j & 31)) & 0xfu) : 0xfu;
+            if ((unsigned)(self_col - j) < 4u) ok &= ~(1u << (self_col - j));
+            if (ok & 1u) f(v.x, j);
+            if (ok & 2u) f(v.y, j + 1);
+            if (ok & 4u) f(v.z, j + 2);
+            if (ok & 8u) f(v.w, j + 3);
+        }
+        const int j = (n4 << 2) + tid;
+        if (j < n_cols && j != self_col && tk_allowed(mask, j)) f(__ldg(d + j), j);
+    } else {
+#pragma unroll 4
+        for (int j = tid; j < n_cols; j += TK_THREADS)
+            if (j != self_col && tk_allowed(mask, j)) f(__ldg(d + j), j);
+    }
+}
+
+template <bool VEC4>
+__global__ void __launch_bounds__(TK_THREADS)
+topk_rows_kernel(const float* __restrict__ D, int64_t ld, int n_cols, int k, int self_col0,
+                 const uint32_t* __restrict__ mask, int32_t* __restrict__ idx_out,
+                 float* __restrict__ val_out) {
+    __shared__ __align__(16) float tmin[TK_THREADS];
+    __shared__ float cand_v[TK_CAND];
+    __shared__ int cand_i[TK_CAND];
+    __shared__ float bound;
+    __shared__ int n_cand;
+
+    const int row = blockIdx.x;
+    const float* d = D + (int64_t)row * ld;
+    const int self_col = self_col0 + row;      // excluded: a node is not its own neighbour
+    const int tid = threadIdx.x;
+
+    // ---- pass 1: per-thread minimum ----
+    float mine = INFINITY;
+    tk_stream_row<VEC4>(d, n_cols, self_col, mask, [&](float v, int) { mine = fminf(mine, v); });
+    // ---- bound = k-th smallest of the THREADS minima ----
+    // Each warp sorts its 32 minima with shuffles; a thread then ranks its own value against the
+    // 8 sorted lists by binary search: lt = #minima below it, le = #minima not above it.  The value
+    // with lt <= k-1 < le is the k-th smallest (every thread holding it writes the same bound).
+    // Threads without an element hold +inf; if fewer than k threads have one, the bound is +inf
+    // and the whole (then short) row becomes the candidate list.
+    {
+        const int lane = tid & 31;
+        float x = mine;
+#pragma unroll
+        for (int sz = 2; sz <= 32; sz <<= 1) {
+#pragma unroll
+            for (int st = sz >> 1; st > 0; st >>= 1) {
+                const float y = __shfl_xor_sync(0xffffffffu, x, st);
+                const bool up = ((lane & sz) == 0);
+                const bool lower = ((lane & st) == 0);
+                x = (lower == up) ? fminf(x, y) : fmaxf(x, y);
+            }
+        }
+        tmin[tid] = x;                          // warp w's minima, ascending, at tmin[32 w ..]
+        if (tid == 0) { n_cand = 0; bound = INFINITY; }
+        __syncthreads();
+        int lt = 0, le = 0;
+#pragma unroll
+        for (int w = 0; w < TK_THREADS / 32; ++w) {
+            const float* a = tmin + 32 * w;
+            int p = 0, q = 0;
+#pragma unroll
+            for (int s2 = 16; s2 >= 1; s2 >>= 1) {
+                if (a[p + s2 - 1] < x) p += s2;
+                if (a[q + s2 - 1] <= x) q += s2;
+            }
+            p += (a[p] < x) ? 1 : 0;
+            q += (a[q] <= x) ? 1 : 0;
+            lt += p;
+            le += q;
+        }
+        if (lt <= k - 1 && k - 1 < le) bound = x;
+    }
+    __syncthreads();
+    // ---- pass 2: everything <= bound is a candidate ----
+    const float T = bound;
+    tk_stream_row<VEC4>(d, n_cols, self_col, mask, [&](float v, int j) {
+        if (v <= T) {
+            const int p = atomicAdd(&n_cand, 1);
+            if (p < TK_CAND) { cand_v[p] = v; cand_i[p] = j; }
+        }
+    });
+    __syncthreads();
+    const int nc = n_cand;
+    if (nc > TK_CAND) {                         // uniform: a huge tie class -> exact radix select
+        topk_row_radix(D, ld, n_cols, k, self_col0, mask, idx_out, val_out);
+        return;
+    }
+    // ---- sort the candidates by (distance, column) ----
+    int sz_all = 64;
+    while (sz_all < nc) sz_all <<= 1;
+    for (int i = nc + tid; i < sz_all; i += TK_THREADS) { cand_v[i] = INFINITY; cand_i[i] = 0x7fffffff; }
+    __syncthreads();
+    if (sz_all == 64) {                         // one warp, one compare-exchange per lane and stage
+        if (tid < 32) {
+            for (int sz = 2; sz <= 64; sz <<= 1) {
+                for (int st = sz >> 1; st > 0; st >>= 1) {
+                    const int i = ((tid & ~(st - 1)) << 1) | (tid & (st - 1));
+                    const int o = i | st;
+                    const bool up = ((i & sz) == 0);
+                    const float a = cand_v[i], b = cand_v[o];
+                    const int ia = cand_i[i], ib = cand_i[o];
+                    if (tk_after(a, ia, b, ib) == up) { cand_v[i] = b; cand_v[o] = a; cand_i[i] = ib; cand_i[o] = ia; }
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        for (int sz = 2; sz <= sz_all; sz <<= 1) {
+            for (int st = sz >> 1; st > 0; st >>= 1) {
+                for (int t = tid; t < (sz_all >> 1); t += TK_THREADS) {
+                    const int i = ((t & ~(st - 1)) << 1) | (t & (st - 1));
+                    const int o = i | st;
+                    const bool up = ((i & sz) == 0);
+                    const float a = cand_v[i], b = cand_v[o];
+                    const int ia = cand_i[i], ib = cand_i[o];
+                    if (tk_after(a, ia, b, ib) == up) { cand_v[i] = b; cand_v[o] = a; cand_i[i] = ib; cand_i[o] = ia; }
+                }
+                __syncthreads();
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < k) {
+        val_out[(int64_t)row * k + tid] = (tid < nc) ? cand_v[tid] : INFINITY;
+        idx_out[(int64_t)row * k + tid] = (tid < nc) ? cand_i[tid] : -1;
+    }
+}
+
 }  // namespace hsd
 
 extern "C" int hsd_topk_rows(const float* D, int64_t ld, int32_t n_rows, int32_t n_cols, int32_t k,
@@ -141,8 +309,15 @@ extern "C" int hsd_topk_rows(const float* D, int64_t ld, int32_t n_rows, int32_t
     HSD_REQUIRE(n_rows >= 0 && n_cols > 0 && ld >= n_cols, "bad sizes");
     HSD_REQUIRE(k >= 1 && k <= TK_MAX, "k must be in 1..64");
     if (n_rows == 0) return HSD_OK;
-    topk_rows_kernel<<<n_rows, TK_THREADS, 0, (cudaStream_t)stream>>>(D, ld, n_cols, k, self_col0, col_mask,
-                                                                     idx_out, val_out);
+    static int force_radix = -1;   // test knob: HSD_TOPK_RADIX=1 sends every row through the radix select
+    if (force_radix < 0) { const char* e = getenv("HSD_TOPK_RADIX"); force_radix = (e && atoi(e)) ? 1 : 0; }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (force_radix)
+        topk_rows_radix_kernel<<<n_rows, TK_THREADS, 0, st>>>(D, ld, n_cols, k, self_col0, col_mask, idx_out, val_out);
+    else if ((reinterpret_cast<uintptr_t>(D) & 15) == 0 && (ld & 3) == 0)
+        topk_rows_kernel<true><<<n_rows, TK_THREADS, 0, st>>>(D, ld, n_cols, k, self_col0, col_mask, idx_out, val_out);
+    else
+        topk_rows_kernel<false><<<n_rows, TK_THREADS, 0, st>>>(D, ld, n_cols, k, self_col0, col_mask, idx_out, val_out);
     HSD_CUDA_TRY(cudaGetLastError());
     return HSD_OK;
 }

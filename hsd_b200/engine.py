@@ -93,6 +93,24 @@ class DeviceGraph:
 # --------------------------------------------------------------------------
 # K1/K2
 # --------------------------------------------------------------------------
+_BFS_WS = {}   # device index -> int32 workspace tensor (grow-only), registered with the library
+
+
+def ensure_bfs_workspace(n_nodes: int, device) -> None:
+    """Graphs above ~400k nodes keep the BFS bitmaps in a global workspace (hsd_bfs_workspace_words);
+    allocate / grow it and register it with the library before a BFS launch.  No-op otherwise."""
+    words = int(lib.hsd_bfs_workspace_words(n_nodes))
+    if not words:
+        return
+    dev = torch.device(device)
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    ws = _BFS_WS.get(key)
+    if ws is None or ws.numel() < words:
+        ws = torch.empty(words, dtype=torch.int32, device=dev)
+        _BFS_WS[key] = ws
+    check(lib.hsd_bfs_set_workspace(_ptr(ws), ws.numel()))
+
+
 def ring_signature_degree(dg: DeviceGraph, hops: int, rows: Optional[torch.Tensor] = None,
                           want_sig: bool = True, want_sizes: bool = True,
                           want_bitmaps: bool = False, empty: str = "raise",
@@ -126,6 +144,7 @@ def ring_signature_degree(dg: DeviceGraph, hops: int, rows: Optional[torch.Tenso
     bitmaps = (torch.empty((n_src, hops + 1, dg.n_words), dtype=torch.int32, device=dev)
                if want_bitmaps else None)
     status = torch.zeros(1, dtype=torch.int32, device=dev)
+    ensure_bfs_workspace(dg.n, dev)
     check(lib.hsd_ring_signature_degree(
         _ptr(dg.rowptr), _ptr(dg.col), dg.n, _ptr(src), _ptr(out_rows), n_src, hops,
         _ptr(dg.bin_end), _ptr(dg.delta), dg.n_bins,
@@ -308,6 +327,7 @@ class HostDegreePipeline:
             self.dev_in[k].copy_(v, non_blocking=True)
         d = self.dev_in
         self.status.zero_()
+        ensure_bfs_workspace(self.n, self.dev)
         check(lib.hsd_ring_signature_degree(
             _ptr(d["rowptr"]), _ptr(d["col"]), self.n, _ptr(d["new_of"]), _ptr(self.out_rows_idx), self.n,
             self.hops, _ptr(d["bin_end"]), _ptr(d["delta"]), self.n_bins,

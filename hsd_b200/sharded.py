@@ -94,7 +94,9 @@ class ShardedDegreeHSD:
         # stream while the rest run with the default CTA size.
         self.side = None
         self.hub_split = None
-        if 0 < self.n_src <= 4096:
+        # (not when the BFS bitmaps live in the shared global workspace: two concurrent launches would race on it)
+        from ._lib import lib as _lib_
+        if 0 < self.n_src <= 4096 and int(_lib_.hsd_bfs_workspace_words(n)) == 0:
             deg = (dg.rowptr[1:] - dg.rowptr[:-1])[self.src.long()]
             hub = deg > HUB_DEGREE
             if bool(hub.any()) and not bool(hub.all()):
@@ -134,6 +136,7 @@ class ShardedDegreeHSD:
         dg = self.dg
         if self.n_src == 0:
             return
+        engine.ensure_bfs_workspace(dg.n, dg.rowptr.device)
 
         def launch(src, out_rows, threads, stream):
             if self.sig_peer_ptrs is not None:

@@ -95,6 +95,13 @@ int hsd_ring_signature_degree_allgather(const int32_t* rowptr, const int32_t* co
                                         int32_t* ring_sizes, int32_t empty_as_zero, int32_t* status,
                                         int32_t cta_threads, void* stream);
 
+/* Graphs above ~400k nodes: the four N-bit bitmaps of a source no longer fit shared memory.  The
+ * BFS entry points then use a caller-owned DEVICE workspace of hsd_bfs_workspace_words(n_nodes)
+ * uint32 words (0 = not needed), registered per host thread with hsd_bfs_set_workspace (NULL
+ * unregisters); CTAs become persistent and keep their bitmaps in an L2-resident slice of it. */
+int64_t hsd_bfs_workspace_words(int32_t n_nodes);
+int hsd_bfs_set_workspace(uint32_t* workspace, int64_t words);
+
 /* Rings only (tools/hierarchy.py:25-38, model/HSD.py:87-94 ring sizes). */
 int hsd_bfs_rings(const int32_t* rowptr, const int32_t* col, int32_t n_nodes,
                   const int32_t* src_nodes, const int32_t* out_rows, int32_t n_src,

@@ -125,3 +125,40 @@ def test_c3_sampled_pairs_match_oracle():
     rings = O.all_rings(adj, 4, rows)
     for r in rows:
         assert sizes[r].tolist() == [len(l) for l in rings[r]]
+
+
+def test_bfs_above_the_shared_memory_limit():
+    """450 000 nodes: the four N-bit bitmaps of a source (225 KB) no longer fit shared memory, so
+    the BFS kernel runs its global-workspace variant (persistent CTAs).  Ring sizes and degree
+    signatures of sampled sources against the oracle."""
+    import torch
+    from hsd_b200 import engine
+    from hsd_b200._lib import lib
+    from hsd_b200.graph import powerlaw_graph
+    n, hops = 450000, 2
+    assert lib.hsd_bfs_workspace_words(n) > 0 and lib.hsd_bfs_workspace_words(100000) == 0
+    g = powerlaw_graph(n, 3, seed=0)
+    dg = engine.DeviceGraph.upload(g)
+    rows = torch.tensor([0, 1, 17, 1000, 123456, n - 1] + list(range(5000, 5600)), dtype=torch.int32, device="cuda")
+    sig, sizes, _, status = engine.ring_signature_degree(dg, hops, rows=rows)
+    torch.cuda.synchronize()
+    assert int(status.item()) == 0
+    adj = [g.neighbors(i).astype(np.int64) for i in (0, 1, 17, 1000, 123456, n - 1)]
+    deg = g.degree.astype(np.float64)
+    sup = dg.support
+    for a, src in enumerate((0, 1, 17, 1000, 123456, n - 1)):
+        # hop 1 = neighbours, hop 2 = neighbours of neighbours not seen before (tools/hierarchy.py:25-38)
+        ring1 = set(adj[a].tolist()) - {src}
+        ring2 = set()
+        for v in ring1:
+            ring2.update(g.neighbors(v).tolist())
+        ring2 -= ring1 | {src}
+        assert sizes[a].tolist() == [1, len(ring1), len(ring2)]
+        row = sig[a].cpu().numpy().astype(np.float64)
+        assert row[0] == deg[src]
+        for h, ring in enumerate((ring1, ring2)):
+            d = deg[np.fromiter(ring, dtype=np.int64)]
+            cdf = np.searchsorted(np.sort(d), sup[:-1], side="right") / len(d)
+            want = cdf * np.diff(sup)
+            got = row[1 + h * (len(sup) - 1):1 + (h + 1) * (len(sup) - 1)]
+            np.testing.assert_allclose(got, want, rtol=2e-6, atol=1e-9)

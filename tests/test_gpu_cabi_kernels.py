@@ -167,6 +167,34 @@ def test_topk_rows_matches_stable_argsort(n_rows, n_cols, k):
         assert np.all(np.isinf(val[r, len(order):]))
 
 
+def _topk_expect(D, r, k, n_cols, self_col):
+    order = sorted((j for j in range(n_cols) if j != self_col), key=lambda j: (D[r, j], j))[:k]
+    return order + [-1] * (k - len(order))
+
+
+@pytest.mark.parametrize("n_rows,n_alloc,n_cols,k,levels", [
+    (40, 6000, 6000, 10, 2),      # ~2000 columns tie at the smallest value: > TK_CAND candidates -> radix select
+    (40, 6000, 5998, 64, 3),      # same through the 16-byte path with a ragged tail
+    (50, 1024, 1022, 7, 1000),    # 16-byte loads + 2 tail columns, few ties
+    (33, 1003, 1003, 20, 1000),   # leading dimension not a multiple of 4: scalar loads
+    (20, 20000, 20000, 20, 1 << 20),  # C2 row length, essentially no ties
+])
+def test_topk_rows_two_pass_and_fallback(n_rows, n_alloc, n_cols, k, levels):
+    """The two-pass kernel (per-thread minima -> bound -> candidate list) and its radix fallback give
+    the (distance, column)-ordered k smallest of every row; rows are nodes 5.. so the excluded
+    self column is not the row index."""
+    import torch
+    from hsd_b200 import engine
+    rng = np.random.default_rng(n_alloc + k)
+    D = (np.floor(rng.random((n_rows, n_alloc)) * levels) / 8.0).astype(np.float32)
+    idx, val = engine.topk_rows(torch.from_numpy(D).cuda(), k, self_col0=5, n_cols=n_cols)
+    idx, val = idx.cpu().numpy(), val.cpu().numpy()
+    for r in range(n_rows):
+        want = _topk_expect(D, r, k, n_cols, 5 + r)
+        assert idx[r].tolist() == want
+        assert np.array_equal(val[r], D[r, want])
+
+
 def test_topk_rows_with_column_mask_and_model_api(golden_graphs):
     import torch
     from conftest import nx_graph

@@ -143,6 +143,29 @@ class DynamicHSD(MultiHSD):
         self._pending.clear()
         return self._D
 
+    def structural_distance_update_sharded(self, rank: int, world: int, group=None, peer: bool = True) -> torch.Tensor:
+        """structural_distance_update() on `world` GPUs (one process per GPU, every process applies
+        the same insertions): returns this rank's row block [shard_rows(n, world, rank)] of the
+        matrix, float32 on its device.  The plan (signature table, result block, peer mappings) is
+        kept across updates; ShardedDegreeHSD.update deals the affected rows round-robin and stores
+        them through peer memory.  A new node or a new distinct degree rebuilds the plan (full step)."""
+        if self.signal != "degree":
+            raise NotImplementedError("the sharded incremental update is defined for signal='degree'")
+        from ..sharded import ShardedDegreeHSD
+        dg = self._device_graph(include_zero=(self.empty == "zero"))
+        plan = getattr(self, "_plan", None)
+        reusable = (plan is not None and plan.world == world and plan.rank == rank and plan.dg.n == dg.n
+                    and plan.hops == self.hop and np.array_equal(plan.dg.support, dg.support))
+        if not reusable:
+            self._plan = plan = ShardedDegreeHSD(dg, self.hop, rank, world, group=group, empty=self.empty, peer=peer)
+            blk = plan.step()
+            self.last_affected = torch.arange(dg.n, device=dg.rowptr.device)
+        else:
+            blk, self.last_affected = plan.update(dg)
+        plan.check()
+        self._pending.clear()
+        return blk
+
     # ---- exploratory helpers of the reference ----
     def explore_neighborhoods(self, node, maxHop=5) -> set:
         """model/dynamic_HSD.py:28-43: BFS layers of one node, stored in ``self.hierarchy[node]``;

@@ -82,27 +82,8 @@ class ShardedDegreeHSD:
         else:
             self.sig_all = torch.zeros((world * self.per, self.ld), dtype=torch.float32, device=dev)
         self.sigT = engine.alloc_signature_table(self.k_used, n, dev)
-        # BFS sources are DEALT round-robin (node s -> rank s % world): contiguous blocks would give
-        # one rank all the hubs of a preferential-attachment graph (its BFS then takes 2x longer).
-        # Table row of node s in the gathered table: (s % world) * per + s // world.
-        self.rows = torch.arange(rank, n, world, dtype=torch.int32, device=dev)
-        self.n_src = int(self.rows.numel())
-        self.src = dg.new_of[self.rows.long()].contiguous()
-        self.out_rows = (rank * self.per + torch.arange(self.n_src, dtype=torch.int32, device=dev)).contiguous()
-        # Latency regime (few sources per rank): one hub source is latency-bound inside its CTA and sets
-        # the floor of the whole BFS phase, so hubs (degree > HUB_DEGREE) get 1024-thread CTAs on a side
-        # stream while the rest run with the default CTA size.
         self.side = None
-        self.hub_split = None
-        # (not when the BFS bitmaps live in the shared global workspace: two concurrent launches would race on it)
-        from ._lib import lib as _lib_
-        if 0 < self.n_src <= 4096 and int(_lib_.hsd_bfs_workspace_words(n)) == 0:
-            deg = (dg.rowptr[1:] - dg.rowptr[:-1])[self.src.long()]
-            hub = deg > HUB_DEGREE
-            if bool(hub.any()) and not bool(hub.all()):
-                self.hub_split = (self.src[hub].contiguous(), self.out_rows[hub].contiguous(),
-                                  self.src[~hub].contiguous(), self.out_rows[~hub].contiguous())
-                self.side = torch.cuda.Stream(device=dev)
+        self._plan_sources(dg)
         node = torch.arange(n, dtype=torch.int32, device=dev)
         self.table_row = ((node % world) * self.per + node // world).to(torch.int32).contiguous()
         self.sizes = torch.zeros((world * self.per, hops + 1), dtype=torch.int32, device=dev)
@@ -124,6 +105,33 @@ class ShardedDegreeHSD:
             self.out = self.out_full[:max(self.n_rows, 1), :n]
         else:
             self.out = torch.empty((max(self.n_rows, 1), n), dtype=torch.float32, device=dev)
+
+    def _plan_sources(self, dg: engine.DeviceGraph) -> None:
+        """Deal this rank's BFS sources for graph `dg` (called again by update(): the degree order,
+        hence the relabelled source ids and the hubs, change with the graph)."""
+        n, rank, world = dg.n, self.rank, self.world
+        dev = dg.rowptr.device
+        # BFS sources are DEALT round-robin (node s -> rank s % world): contiguous blocks would give
+        # one rank all the hubs of a preferential-attachment graph (its BFS then takes 2x longer).
+        # Table row of node s in the gathered table: (s % world) * per + s // world.
+        self.rows = torch.arange(rank, n, world, dtype=torch.int32, device=dev)
+        self.n_src = int(self.rows.numel())
+        self.src = dg.new_of[self.rows.long()].contiguous()
+        self.out_rows = (rank * self.per + torch.arange(self.n_src, dtype=torch.int32, device=dev)).contiguous()
+        # Latency regime (few sources per rank): one hub source is latency-bound inside its CTA and sets
+        # the floor of the whole BFS phase, so hubs (degree > HUB_DEGREE) get 1024-thread CTAs on a side
+        # stream while the rest run with the default CTA size.
+        self.hub_split = None
+        # (not when the BFS bitmaps live in the shared global workspace: two concurrent launches would race on it)
+        from ._lib import lib as _lib_
+        if 0 < self.n_src <= 4096 and int(_lib_.hsd_bfs_workspace_words(n)) == 0:
+            deg = (dg.rowptr[1:] - dg.rowptr[:-1])[self.src.long()]
+            hub = deg > HUB_DEGREE
+            if bool(hub.any()) and not bool(hub.all()):
+                self.hub_split = (self.src[hub].contiguous(), self.out_rows[hub].contiguous(),
+                                  self.src[~hub].contiguous(), self.out_rows[~hub].contiguous())
+                if self.side is None:
+                    self.side = torch.cuda.Stream(device=dev)
 
     def ring_sizes(self) -> torch.Tensor:
         """int32[N, hops+1] in node order (valid after gather for world > 1 only for own sources)."""
@@ -215,6 +223,105 @@ class ShardedDegreeHSD:
         elif self.world > 1 and not hasattr(self, "blocks"):
             import torch.distributed as dist
             dist.barrier(group=self.group)
+
+    # ------------------------------------------------------------------
+    # incremental update after edge insertions (BASELINE config 5; SURVEY.md §8 e "Dynamic")
+    # ------------------------------------------------------------------
+    def update(self, dg_new: engine.DeviceGraph) -> Tuple[torch.Tensor, torch.Tensor]:
+        """This rank's row block of the distance matrix of `dg_new` (same node set, edges inserted),
+        recomputing only what changed; returns (block, affected node ids).  See update_finish()."""
+        self.update_begin(dg_new)
+        self.gather()
+        return self.update_finish()
+
+    def update_begin(self, dg_new: engine.DeviceGraph) -> None:
+        """Keep a copy of the gathered signature table, then rebuild this rank's dealt signatures on
+        the edited graph (the BFS kernel stores them into every rank's table in peer mode)."""
+        import numpy as np
+        if dg_new.n != self.dg.n or not np.array_equal(dg_new.support, self.dg.support):
+            raise ValueError("update() needs the same node set and the same set of distinct degrees: every "
+                             "signature changes representation otherwise; build a new plan and step() it")
+        self.sig_prev = self.sig_all.clone()
+        if self.sig_symm is not None:
+            self.sig_symm.barrier()     # no peer stores new rows into a table that is still being copied
+        self.dg = dg_new
+        self._plan_sources(dg_new)
+        self.signatures()
+
+    def update_finish(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        """After gather(): the exact affected set A = nodes whose signature row differs bit for bit
+        from the previous table (identical on every rank: the tables are replicated), then
+
+        * peer mode — the affected rows are dealt round-robin (A[rank::world]); each rank computes
+          its dealt rows against all N columns once and stores every row into its owner's block and,
+          mirrored, as a column into every rank's block through NVLink peer memory.  |A|·N distances
+          are computed once in the whole job, balanced even when A falls into one rank's row block;
+        * fallback (peer=False) — each rank recomputes own rows x A columns and (A ∩ own rows) x all
+          columns locally: no traffic, twice the arithmetic.
+
+        2|A| >= N falls back to the symmetric full matrix.  Bit-equal to a from-scratch step(): every
+        entry comes from the same kernel and the same signature rows, and |a - b| == |b - a|."""
+        n, dev = self.dg.n, self.sig_all.device
+        changed = (self.sig_all != self.sig_prev).any(dim=1)
+        self.sig_prev = None
+        aff = torch.nonzero(changed[self.table_row.long()], as_tuple=False).reshape(-1)   # node ids, ascending
+        self.last_affected = aff
+        m = int(aff.numel())
+        if m == 0:
+            if self.peer:
+                self.peer_barrier()
+            return self.out[:self.n_rows], aff
+        if 2 * m >= n:
+            return self.distances(), aff
+        n4 = engine.roundup(n, 4)
+        dealt = self.peer or self.world == 1      # one GPU: its own block is the only "peer"
+        cols = aff[self.rank::self.world].contiguous() if dealt else aff
+        mq = int(cols.numel())
+        # table = [all nodes in node order | the affected nodes this rank works on]
+        sigT = engine.alloc_signature_table(self.k_used, n4 + max(mq, 1), dev)
+        engine.signature_transpose(self.sig_all, self.k_used, sigT, 0, src_rows=self.table_row)
+        if mq:
+            engine.signature_transpose(self.sig_all, self.k_used, sigT, n4,
+                                       src_rows=self.table_row[cols].contiguous())
+        n_tab = n4 + max(mq, 1)
+        if dealt:
+            if mq:
+                blk = engine.pairwise_l1(sigT, n_tab, row0=n4, n_rows=mq, col0=0, n_cols=n, symmetric=False,
+                                         k_used=self.k_used)
+                for r, Dr in enumerate(self._block_views()):
+                    r0, nr, _ = shard_rows(n, self.world, r)
+                    if nr == 0:
+                        continue
+                    Dr[:nr].index_copy_(1, cols, blk[:, r0:r0 + nr].t())           # mirrored: columns A_q of every block
+                    lo, hi = (int(x) for x in torch.searchsorted(cols, torch.tensor([r0, r0 + nr], device=dev)))
+                    if hi > lo:
+                        Dr[:, :n].index_copy_(0, cols[lo:hi] - r0, blk[lo:hi])     # direct: rows of A_q this rank owns
+            if self.peer:
+                self.peer_barrier()
+        elif self.n_rows:
+            rect = engine.pairwise_l1(sigT, n_tab, row0=self.row0, n_rows=self.n_rows, col0=n4, n_cols=mq,
+                                      symmetric=False, k_used=self.k_used)
+            self.out[:self.n_rows].index_copy_(1, cols, rect)
+            lo, hi = (int(x) for x in torch.searchsorted(cols, torch.tensor([self.row0, self.row0 + self.n_rows],
+                                                                             device=dev)))
+            if hi > lo:
+                lo4 = lo // 4 * 4       # TMA tile origins are 16-byte aligned
+                rows = engine.pairwise_l1(sigT, n_tab, row0=n4 + lo4, n_rows=hi - lo4, col0=0, n_cols=n,
+                                          symmetric=False, k_used=self.k_used)
+                self.out.index_copy_(0, cols[lo:hi] - self.row0, rows[lo - lo4:])
+        return self.out[:self.n_rows], aff
+
+    def _block_views(self):
+        """Every rank's result block as a tensor on this device (peer mode)."""
+        if hasattr(self, "blocks"):
+            return self.blocks
+        if self.world == 1:
+            return [self.out]
+        if getattr(self, "_views", None) is None:
+            self._views = [self.out_full if r == self.rank else
+                           self.symm.get_buffer(r, (self.per, self.ld_out), torch.float32)
+                           for r in range(self.world)]
+        return self._views
 
     def step(self) -> torch.Tensor:
         self.signatures()

@@ -77,3 +77,100 @@ def test_explore_neighborhoods_and_subgraph():
     sub = m.convert_neighborhoods_to_subgraph(set(ref[0] + ref[1]))
     assert set(sub.nodes()) <= set(ref[0] + ref[1])
     assert all(g.has_edge(u, v) for u, v in sub.edges())
+
+
+def _low_degree_insertions(g, k, seed=3):
+    """Edges between nodes of degree <= 6: the set of distinct degrees (the shared support) stays
+    the same, so the update takes the incremental path instead of a full recompute."""
+    deg = dict(g.degree())
+    low = [v for v in g if deg[v] <= 6]
+    rng = np.random.default_rng(seed)
+    out = set()
+    while len(out) < k:
+        u, v = (int(x) for x in rng.choice(low, 2, replace=False))
+        if not g.has_edge(u, v):
+            out.add((min(u, v), max(u, v)))
+    return sorted(out)
+
+
+@pytest.mark.parametrize("world,peer", [(1, False), (2, False), (3, False), (2, True), (4, True)])
+def test_sharded_incremental_update_equals_from_scratch(world, peer):
+    """Config 5 across ranks (SURVEY §8 e "Dynamic"), the ranks emulated in one process: after the
+    insertions every rank's row block equals the rows of a from-scratch single-GPU matrix bit for
+    bit, in the collective-free fallback (own rows x affected columns + affected own rows) and in
+    peer mode (affected rows dealt round-robin, stored direct + mirrored into the owners' blocks)."""
+    import torch
+    from hsd_b200 import engine
+    from hsd_b200.graph import CSRGraph
+    from hsd_b200.sharded import ShardedDegreeHSD, shard_rows
+    n, hop = 3000, 2
+    g0 = _ba(n)
+    edges = _low_degree_insertions(g0, 4)
+    g1 = g0.copy()
+    g1.add_edges_from(edges)
+    dg0 = engine.DeviceGraph.upload(CSRGraph.from_networkx(g0))
+    dg1 = engine.DeviceGraph.upload(CSRGraph.from_networkx(g1))
+    assert np.array_equal(dg0.support, dg1.support)
+    fresh = ShardedDegreeHSD(dg1, hop, 0, 1).step().clone()
+    before = ShardedDegreeHSD(dg0, hop, 0, 1).step().clone()
+
+    per = shard_rows(n, world, 0)[2]
+    ld = engine.roundup(n, 4)
+    if peer:
+        blocks = [torch.full((per, ld), float("nan"), dtype=torch.float32, device="cuda") for _ in range(world)]
+        plans = [ShardedDegreeHSD(dg0, hop, r, world, peer=True, peer_blocks=blocks) for r in range(world)]
+    else:
+        plans = [ShardedDegreeHSD(dg0, hop, r, world) for r in range(world)]
+
+    def exchange():                       # what the all-gather / the fused peer stores do
+        for p in plans:
+            for q in plans:
+                if p is not q:
+                    sl = slice(q.rank * q.per, q.rank * q.per + q.n_src)
+                    p.sig_all[sl] = q.sig_all[sl]
+
+    def assembled():
+        if peer:
+            return torch.cat([b[:, :n] for b in blocks], 0)[:n]
+        return torch.cat([p.out[:p.n_rows] for p in plans], 0)
+
+    for p in plans:
+        p.signatures()
+    exchange()
+    for p in plans:
+        p.distances()
+    torch.cuda.synchronize()
+    assert torch.equal(assembled(), before)
+
+    for p in plans:
+        p.update_begin(dg1)
+    exchange()
+    affs = [p.update_finish()[1] for p in plans]
+    torch.cuda.synchronize()
+    m = int(affs[0].numel())
+    assert all(torch.equal(a, affs[0]) for a in affs)
+    assert 0 < m and 2 * m < n            # the incremental branch, not the full-matrix fallback
+    assert torch.equal(assembled(), fresh)
+    changed = (before != fresh).cpu().numpy()
+    mask = np.zeros(n, dtype=bool)
+    mask[affs[0].cpu().numpy()] = True
+    assert not changed[~mask][:, ~mask].any()
+    assert changed.any()
+
+
+def test_dynamic_model_sharded_api_single_rank():
+    """DynamicHSD.structural_distance_update_sharded on one rank: first call = full step, second =
+    incremental update through the kept plan; both equal the unsharded method."""
+    import torch
+    from model import DynamicHSD
+    g0 = _ba(2000)
+    edges = _low_degree_insertions(g0, 3)
+    a = DynamicHSD(g0.copy(), "ba", 2, 1, "wasserstein", signal="degree")
+    b = DynamicHSD(g0.copy(), "ba", 2, 1, "wasserstein", signal="degree")
+    assert torch.equal(a.structural_distance_update_sharded(0, 1), b.structural_distance_update())
+    a.dynamic_add_edges(edges)
+    b.dynamic_add_edges(edges)
+    Da, Db = a.structural_distance_update_sharded(0, 1), b.structural_distance_update()
+    assert torch.equal(Da, Db)
+    assert torch.equal(torch.sort(a.last_affected).values, torch.sort(b.last_affected).values)
+    assert 0 < a.last_affected.numel() < 1000

@@ -10,6 +10,7 @@
 // coalesced 128-byte requests; all scales share T_k and are accumulated in the
 // same pass.  FP64 throughout: the SpMM is bandwidth-bound and FP32 cannot hold
 // 1e-5 relative on coefficients that span nine orders of magnitude.
+#include <stdlib.h>
 #include "hsd_common.cuh"
 
 namespace hsd {
@@ -23,8 +24,12 @@ struct ChebArgs {
     int k, order, n_scales;
     double a;          // lmax / 2
     double threshold;
-    double ck[MAX_SCALES];   // c_{s,k}
-    double c0[MAX_SCALES];   // c_{s,0} (used at k == 1)
+    // Accumulation is DEFERRED: a thread holds T_k, T_{k-1} and T_{k-2} of its element anyway, so the
+    // S accumulators are read-modify-written only every third step (acc != 0) with three terms at
+    // once: out_s += w2[s] T_{k-2} + w1[s] T_{k-1} + w0[s] T_k (weights of terms already added are 0;
+    // the k = 0 term carries c_{s,0}/2).  acc_first: nothing accumulated yet, do not read out.
+    int acc, acc_first;
+    double w0[MAX_SCALES], w1[MAX_SCALES], w2[MAX_SCALES];
     const double* t_prev;    // T_{k-1}
     const double* t_prev2;   // T_{k-2} (k >= 2)
     double* t_new;
@@ -87,24 +92,26 @@ __global__ void __launch_bounds__(256) cheb_step_kernel(const ChebArgs p) {
     double2 t;  // ((L - a I) T_{k-1})[v][c..c+1], then the recurrence
     t.x = dm * tp.x - nb.x;
     t.y = dm * tp.y - nb.y;
+    double2 t2 = make_double2(0.0, 0.0);
     if (p.k == 1) {
         t.x /= p.a; t.y /= p.a;
     } else {
-        const double2 t2 = ld_cs(p.t_prev2 + idx);
+        t2 = ld_cs(p.t_prev2 + idx);
         t.x = (2.0 / p.a) * t.x - t2.x;
         t.y = (2.0 / p.a) * t.y - t2.y;
     }
     *reinterpret_cast<double2*>(p.t_new + idx) = t;
+    if (!p.acc) return;
     const int64_t plane = (int64_t)p.n_nodes * p.n_cols;
     const bool last = (p.k == p.order);
 #pragma unroll
     for (int s = 0; s < MAX_SCALES; ++s) {
         if (s >= p.n_scales) break;
-        double2 r;
-        if (p.k == 1) { r.x = 0.5 * p.c0[s] * tp.x; r.y = 0.5 * p.c0[s] * tp.y; }
-        else r = ld_cs(p.out + s * plane + idx);
-        r.x += p.ck[s] * t.x;
-        r.y += p.ck[s] * t.y;
+        double2 r = make_double2(0.0, 0.0);
+        if (!p.acc_first) r = ld_cs(p.out + s * plane + idx);
+        r.x += p.w2[s] * t2.x; r.y += p.w2[s] * t2.y;      // ascending k, like the oracle's running sum
+        r.x += p.w1[s] * tp.x; r.y += p.w1[s] * tp.y;
+        r.x += p.w0[s] * t.x;  r.y += p.w0[s] * t.y;
         if (last) {  // model/HSD.py:65
             r.x = (r.x > p.threshold) ? r.x : 0.0;
             r.y = (r.y > p.threshold) ? r.y : 0.0;
@@ -246,10 +253,24 @@ extern "C" int hsd_cheb_spmm(const int32_t* rowptr, const int32_t* col, int32_t 
     ChebArgs a;
     a.rowptr = rowptr; a.col = col; a.n_nodes = n_nodes; a.n_cols = n_cols; a.col0 = col0;
     a.order = order; a.n_scales = n_scales; a.a = lmax / 2.0; a.threshold = threshold; a.out = out;
-    for (int s = 0; s < n_scales; ++s) a.c0[s] = coeff_host[(int64_t)s * (order + 1)];
+    static int every = -1;   // tuning knob: HSD_CHEB_ACC_EVERY=1 accumulates at every step (the first version)
+    if (every < 0) { const char* e = getenv("HSD_CHEB_ACC_EVERY"); every = e ? atoi(e) : 3; if (every < 1 || every > 3) every = 3; }
+    int next_term = 0;       // lowest k whose c_k T_k has not been added to the accumulators yet
     for (int k = 1; k <= order; ++k) {
         a.k = k;
-        for (int s = 0; s < n_scales; ++s) a.ck[s] = coeff_host[(int64_t)s * (order + 1) + k];
+        // accumulate at k = 2, 5, 8, ... (terms k-2..k, all in registers at that step) and at the last step
+        a.acc = (k == order || k % every == every - 1) ? 1 : 0;
+        a.acc_first = (next_term == 0) ? 1 : 0;
+        if (a.acc) {
+            for (int s = 0; s < n_scales; ++s) {
+                const double* cs = coeff_host + (int64_t)s * (order + 1);
+                auto w = [&](int j) { return j < next_term ? 0.0 : (j == 0 ? 0.5 * cs[0] : cs[j]); };
+                a.w0[s] = w(k);
+                a.w1[s] = w(k - 1);
+                a.w2[s] = (k >= 2) ? w(k - 2) : 0.0;
+            }
+            next_term = k + 1;
+        }
         a.t_prev = T[(k - 1) % 3];
         a.t_prev2 = T[(k + 1) % 3];  // == (k-2) mod 3
         a.t_new = T[k % 3];

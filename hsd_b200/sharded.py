@@ -20,6 +20,7 @@ model pickled per task (model/HSD.py:118-137).
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -83,6 +84,7 @@ class ShardedDegreeHSD:
             self.sig_all = torch.zeros((world * self.per, self.ld), dtype=torch.float32, device=dev)
         self.sigT = engine.alloc_signature_table(self.k_used, n, dev)
         self.side = None
+        self.update_mode = os.environ.get("HSD_DYN_PEER_MODE", "rows")   # see update_finish()
         self._plan_sources(dg)
         node = torch.arange(n, dtype=torch.int32, device=dev)
         self.table_row = ((node % world) * self.per + node // world).to(torch.int32).contiguous()
@@ -252,12 +254,16 @@ class ShardedDegreeHSD:
         """After gather(): the exact affected set A = nodes whose signature row differs bit for bit
         from the previous table (identical on every rank: the tables are replicated), then
 
-        * peer mode — the affected rows are dealt round-robin (A[rank::world]); each rank computes
-          its dealt rows against all N columns once and stores every row into its owner's block and,
-          mirrored, as a column into every rank's block through NVLink peer memory.  |A|·N distances
-          are computed once in the whole job, balanced even when A falls into one rank's row block;
+        * peer mode, update_mode "rows" (default) — every rank recomputes the COLUMNS A of its own row
+          block locally; the ROWS of A are dealt round-robin (A[rank::world]), computed against all N
+          columns and stored whole into their owners' blocks through NVLink peer memory (contiguous
+          rows: coalesced stores).  2·|A|·N distances in the job, balanced even when A falls into one
+          rank's row block;
+        * peer mode, update_mode "mirror" (HSD_DYN_PEER_MODE=mirror; also the one-GPU case) — dealt
+          rows only, each also stored mirrored as a column into every rank's block: |A|·N distances,
+          but the mirrored half is a scatter of 4-byte peer stores;
         * fallback (peer=False) — each rank recomputes own rows x A columns and (A ∩ own rows) x all
-          columns locally: no traffic, twice the arithmetic.
+          columns locally: no traffic, 2·|A|·N distances, unbalanced if A is concentrated.
 
         2|A| >= N falls back to the symmetric full matrix.  Bit-equal to a from-scratch step(): every
         entry comes from the same kernel and the same signature rows, and |a - b| == |b - a|."""
@@ -274,41 +280,74 @@ class ShardedDegreeHSD:
         if 2 * m >= n:
             return self.distances(), aff
         n4 = engine.roundup(n, 4)
-        dealt = self.peer or self.world == 1      # one GPU: its own block is the only "peer"
-        cols = aff[self.rank::self.world].contiguous() if dealt else aff
-        mq = int(cols.numel())
-        # table = [all nodes in node order | the affected nodes this rank works on]
-        sigT = engine.alloc_signature_table(self.k_used, n4 + max(mq, 1), dev)
-        engine.signature_transpose(self.sig_all, self.k_used, sigT, 0, src_rows=self.table_row)
-        if mq:
-            engine.signature_transpose(self.sig_all, self.k_used, sigT, n4,
-                                       src_rows=self.table_row[cols].contiguous())
-        n_tab = n4 + max(mq, 1)
-        if dealt:
+        mode = "local"
+        if self.world == 1:
+            mode = "mirror"                       # one GPU: its own block is the only "peer"
+        elif self.peer:
+            mode = self.update_mode               # "rows" (default) or "mirror"
+        k = self.k_used
+        tbl_all = self.table_row
+
+        def direct_rows(dealt, blk):
+            """Full rows (contiguous, coalesced peer stores) of the dealt affected nodes -> their owners."""
+            for r, Dr in enumerate(self._block_views()):
+                r0, nr, _ = shard_rows(n, self.world, r)
+                lo, hi = (int(x) for x in torch.searchsorted(dealt, torch.tensor([r0, r0 + nr], device=dev)))
+                if hi > lo:
+                    Dr[:, :n].index_copy_(0, dealt[lo:hi] - r0, blk[lo:hi])
+
+        if mode == "mirror":
+            # table = [all nodes | dealt affected nodes]; each distance computed once in the job; the
+            # mirrored half is a 4-byte scatter into every block (peer stores when world > 1)
+            dealt = aff[self.rank::self.world].contiguous()
+            mq = int(dealt.numel())
             if mq:
-                blk = engine.pairwise_l1(sigT, n_tab, row0=n4, n_rows=mq, col0=0, n_cols=n, symmetric=False,
-                                         k_used=self.k_used)
+                sigT = engine.alloc_signature_table(k, n4 + mq, dev)
+                engine.signature_transpose(self.sig_all, k, sigT, 0, src_rows=tbl_all)
+                engine.signature_transpose(self.sig_all, k, sigT, n4, src_rows=tbl_all[dealt].contiguous())
+                blk = engine.pairwise_l1(sigT, n4 + mq, row0=n4, n_rows=mq, col0=0, n_cols=n, symmetric=False, k_used=k)
                 for r, Dr in enumerate(self._block_views()):
                     r0, nr, _ = shard_rows(n, self.world, r)
-                    if nr == 0:
-                        continue
-                    Dr[:nr].index_copy_(1, cols, blk[:, r0:r0 + nr].t())           # mirrored: columns A_q of every block
-                    lo, hi = (int(x) for x in torch.searchsorted(cols, torch.tensor([r0, r0 + nr], device=dev)))
-                    if hi > lo:
-                        Dr[:, :n].index_copy_(0, cols[lo:hi] - r0, blk[lo:hi])     # direct: rows of A_q this rank owns
-            if self.peer:
-                self.peer_barrier()
+                    if nr:
+                        Dr[:nr].index_copy_(1, dealt, blk[:, r0:r0 + nr].t())
+                direct_rows(dealt, blk)
+        elif mode == "rows":
+            # table = [all nodes | all affected nodes | pad | dealt affected nodes]: the COLUMNS of the
+            # affected nodes are recomputed by every rank for its own rows (local scatter); their ROWS are
+            # dealt round-robin and stored whole into the owners' blocks (coalesced peer stores)
+            dealt = aff[self.rank::self.world].contiguous()
+            mq = int(dealt.numel())
+            m4 = engine.roundup(m, 4)
+            sigT = engine.alloc_signature_table(k, n4 + m4 + max(mq, 1), dev)
+            engine.signature_transpose(self.sig_all, k, sigT, 0, src_rows=tbl_all)
+            engine.signature_transpose(self.sig_all, k, sigT, n4, src_rows=tbl_all[aff].contiguous())
+            n_tab = sigT.shape[1]
+            if self.n_rows:
+                rect = engine.pairwise_l1(sigT, n_tab, row0=self.row0, n_rows=self.n_rows, col0=n4, n_cols=m,
+                                          symmetric=False, k_used=k)
+                self.out[:self.n_rows].index_copy_(1, aff, rect)
+            if mq:
+                engine.signature_transpose(self.sig_all, k, sigT, n4 + m4, src_rows=tbl_all[dealt].contiguous())
+                blk = engine.pairwise_l1(sigT, n_tab, row0=n4 + m4, n_rows=mq, col0=0, n_cols=n, symmetric=False,
+                                         k_used=k)
+                direct_rows(dealt, blk)
         elif self.n_rows:
-            rect = engine.pairwise_l1(sigT, n_tab, row0=self.row0, n_rows=self.n_rows, col0=n4, n_cols=mq,
-                                      symmetric=False, k_used=self.k_used)
-            self.out[:self.n_rows].index_copy_(1, cols, rect)
-            lo, hi = (int(x) for x in torch.searchsorted(cols, torch.tensor([self.row0, self.row0 + self.n_rows],
-                                                                             device=dev)))
+            # no peer memory: own rows x affected columns, then (affected ∩ own rows) x all columns
+            sigT = engine.alloc_signature_table(k, n4 + m, dev)
+            engine.signature_transpose(self.sig_all, k, sigT, 0, src_rows=tbl_all)
+            engine.signature_transpose(self.sig_all, k, sigT, n4, src_rows=tbl_all[aff].contiguous())
+            rect = engine.pairwise_l1(sigT, n4 + m, row0=self.row0, n_rows=self.n_rows, col0=n4, n_cols=m,
+                                      symmetric=False, k_used=k)
+            self.out[:self.n_rows].index_copy_(1, aff, rect)
+            lo, hi = (int(x) for x in torch.searchsorted(aff, torch.tensor([self.row0, self.row0 + self.n_rows],
+                                                                            device=dev)))
             if hi > lo:
                 lo4 = lo // 4 * 4       # TMA tile origins are 16-byte aligned
-                rows = engine.pairwise_l1(sigT, n_tab, row0=n4 + lo4, n_rows=hi - lo4, col0=0, n_cols=n,
-                                          symmetric=False, k_used=self.k_used)
-                self.out.index_copy_(0, cols[lo:hi] - self.row0, rows[lo - lo4:])
+                rows = engine.pairwise_l1(sigT, n4 + m, row0=n4 + lo4, n_rows=hi - lo4, col0=0, n_cols=n,
+                                          symmetric=False, k_used=k)
+                self.out.index_copy_(0, aff[lo:hi] - self.row0, rows[lo - lo4:])
+        if self.peer:
+            self.peer_barrier()
         return self.out[:self.n_rows], aff
 
     def _block_views(self):

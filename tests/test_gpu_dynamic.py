@@ -93,12 +93,14 @@ def _low_degree_insertions(g, k, seed=3):
     return sorted(out)
 
 
-@pytest.mark.parametrize("world,peer", [(1, False), (2, False), (3, False), (2, True), (4, True)])
-def test_sharded_incremental_update_equals_from_scratch(world, peer):
+@pytest.mark.parametrize("world,peer,mode", [(1, False, None), (2, False, None), (3, False, None),
+                                             (2, True, "rows"), (4, True, "rows"), (3, True, "mirror")])
+def test_sharded_incremental_update_equals_from_scratch(world, peer, mode):
     """Config 5 across ranks (SURVEY §8 e "Dynamic"), the ranks emulated in one process: after the
     insertions every rank's row block equals the rows of a from-scratch single-GPU matrix bit for
     bit, in the collective-free fallback (own rows x affected columns + affected own rows) and in
-    peer mode (affected rows dealt round-robin, stored direct + mirrored into the owners' blocks)."""
+    both peer modes (affected rows dealt round-robin and stored whole into the owners' blocks, their
+    columns either recomputed locally — "rows" — or stored mirrored — "mirror")."""
     import torch
     from hsd_b200 import engine
     from hsd_b200.graph import CSRGraph
@@ -119,6 +121,8 @@ def test_sharded_incremental_update_equals_from_scratch(world, peer):
     if peer:
         blocks = [torch.full((per, ld), float("nan"), dtype=torch.float32, device="cuda") for _ in range(world)]
         plans = [ShardedDegreeHSD(dg0, hop, r, world, peer=True, peer_blocks=blocks) for r in range(world)]
+        for p in plans:
+            p.update_mode = mode
     else:
         plans = [ShardedDegreeHSD(dg0, hop, r, world) for r in range(world)]
 

@@ -41,6 +41,22 @@ def shard_rows(n: int, world: int, rank: int) -> Tuple[int, int, int]:
     return row0, max(0, min(per, n - row0)), per
 
 
+def deal_affected(aff: torch.Tensor, n: int, world: int, rank: int):
+    """Incremental update: the affected nodes `aff` (ascending ids, identical on every rank) are dealt
+    round-robin; returns (dealt, segments) with dealt = aff[rank::world] and segments a list of
+    (owner, lo, hi, row0_of_owner): dealt[lo:hi] are the rows owned by `owner` (row blocks are
+    contiguous, dealt is ascending, so each owner's share is one slice)."""
+    dealt = aff[rank::world].contiguous()
+    segments = []
+    if dealt.numel():
+        bounds = [shard_rows(n, world, r)[0] for r in range(world)] + [n]
+        cut = torch.searchsorted(dealt, torch.tensor(bounds, dtype=dealt.dtype, device=dealt.device)).tolist()
+        for r in range(world):
+            if cut[r + 1] > cut[r]:
+                segments.append((r, cut[r], cut[r + 1], bounds[r]))
+    return dealt, segments
+
+
 class ShardedDegreeHSD:
     """Plan + buffers for repeated evaluation of one graph on `world` ranks."""
 
@@ -288,18 +304,16 @@ class ShardedDegreeHSD:
         k = self.k_used
         tbl_all = self.table_row
 
-        def direct_rows(dealt, blk):
+        def direct_rows(dealt, segments, blk):
             """Full rows (contiguous, coalesced peer stores) of the dealt affected nodes -> their owners."""
-            for r, Dr in enumerate(self._block_views()):
-                r0, nr, _ = shard_rows(n, self.world, r)
-                lo, hi = (int(x) for x in torch.searchsorted(dealt, torch.tensor([r0, r0 + nr], device=dev)))
-                if hi > lo:
-                    Dr[:, :n].index_copy_(0, dealt[lo:hi] - r0, blk[lo:hi])
+            views = self._block_views()
+            for r, lo, hi, r0 in segments:
+                views[r][:, :n].index_copy_(0, dealt[lo:hi] - r0, blk[lo:hi])
 
         if mode == "mirror":
             # table = [all nodes | dealt affected nodes]; each distance computed once in the job; the
             # mirrored half is a 4-byte scatter into every block (peer stores when world > 1)
-            dealt = aff[self.rank::self.world].contiguous()
+            dealt, segments = deal_affected(aff, n, self.world, self.rank)
             mq = int(dealt.numel())
             if mq:
                 sigT = engine.alloc_signature_table(k, n4 + mq, dev)
@@ -310,12 +324,12 @@ class ShardedDegreeHSD:
                     r0, nr, _ = shard_rows(n, self.world, r)
                     if nr:
                         Dr[:nr].index_copy_(1, dealt, blk[:, r0:r0 + nr].t())
-                direct_rows(dealt, blk)
+                direct_rows(dealt, segments, blk)
         elif mode == "rows":
             # table = [all nodes | all affected nodes | pad | dealt affected nodes]: the COLUMNS of the
             # affected nodes are recomputed by every rank for its own rows (local scatter); their ROWS are
             # dealt round-robin and stored whole into the owners' blocks (coalesced peer stores)
-            dealt = aff[self.rank::self.world].contiguous()
+            dealt, segments = deal_affected(aff, n, self.world, self.rank)
             mq = int(dealt.numel())
             m4 = engine.roundup(m, 4)
             sigT = engine.alloc_signature_table(k, n4 + m4 + max(mq, 1), dev)
@@ -330,7 +344,7 @@ class ShardedDegreeHSD:
                 engine.signature_transpose(self.sig_all, k, sigT, n4 + m4, src_rows=tbl_all[dealt].contiguous())
                 blk = engine.pairwise_l1(sigT, n_tab, row0=n4 + m4, n_rows=mq, col0=0, n_cols=n, symmetric=False,
                                          k_used=k)
-                direct_rows(dealt, blk)
+                direct_rows(dealt, segments, blk)
         elif self.n_rows:
             # no peer memory: own rows x affected columns, then (affected ∩ own rows) x all columns
             sigT = engine.alloc_signature_table(k, n4 + m, dev)

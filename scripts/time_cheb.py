@@ -17,3 +17,4 @@ for it in range(3):
     ms = a.elapsed_time(b)
     byts = order * (8.0 * g.nnz + 4 * (n + 1) + (3 + 2 * S) * 8.0 * n * C)
     print(f"cheb n={n} order={order} S={S} C={C}: {ms:.3f} ms, {ms/C*1e3:.1f} us/col, alg {byts/ms/1e6:.0f} GB/s")
+print(f"checksum {float(out.sum()):.12e} abs {float(out.abs().sum()):.12e}")

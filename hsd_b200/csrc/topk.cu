@@ -157,11 +157,30 @@ __device__ __forceinline__ bool tk_after(float a, int ia, float b, int ib) {
 }
 
 // Streams the row once: f(value, column) for every admissible column.  VEC4: 16-byte loads (row
-// start 16-byte aligned); the 4 mask bits of a group sit in one bitmap word.
-template <bool VEC4, typename F>
+// start 16-byte aligned); the 4 mask bits of a group sit in one bitmap word.  PLAIN: no column mask
+// and the self column is NOT filtered here (the caller accounts for it), so the loop is loads + f.
+template <bool VEC4, bool PLAIN, typename F>
 __device__ __forceinline__ void tk_stream_row(const float* __restrict__ d, int n_cols, int self_col,
                                               const uint32_t* __restrict__ mask, F f) {
     const int tid = threadIdx.x;
+    if (PLAIN) {
+        if (VEC4) {
+            const int n4 = n_cols >> 2;
+            const float4* d4 = reinterpret_cast<const float4*>(d);
+#pragma unroll 4
+            for (int g = tid; g < n4; g += TK_THREADS) {
+                const float4 v = __ldg(d4 + g);
+                const int j = g << 2;
+                f(v.x, j); f(v.y, j + 1); f(v.z, j + 2); f(v.w, j + 3);
+            }
+            const int j = (n4 << 2) + tid;
+            if (j < n_cols) f(__ldg(d + j), j);
+        } else {
+#pragma unroll 4
+            for (int j = tid; j < n_cols; j += TK_THREADS) f(__ldg(d + j), j);
+        }
+        return;
+    }
     if (VEC4) {
         const int n4 = n_cols >> 2;
         const float4* d4 = reinterpret_cast<const float4*>(d);
@@ -185,7 +204,7 @@ __device__ __forceinline__ void tk_stream_row(const float* __restrict__ d, int n
     }
 }
 
-template <bool VEC4>
+template <bool VEC4, bool PLAIN>
 __global__ void __launch_bounds__(TK_THREADS)
 topk_rows_kernel(const float* __restrict__ D, int64_t ld, int n_cols, int k, int self_col0,
                  const uint32_t* __restrict__ mask, int32_t* __restrict__ idx_out,
@@ -203,7 +222,10 @@ topk_rows_kernel(const float* __restrict__ D, int64_t ld, int n_cols, int k, int
 
     // ---- pass 1: per-thread minimum ----
     float mine = INFINITY;
-    tk_stream_row<VEC4>(d, n_cols, self_col, mask, [&](float v, int) { mine = fminf(mine, v); });
+    tk_stream_row<VEC4, PLAIN>(d, n_cols, self_col, mask, [&](float v, int) { mine = fminf(mine, v); });
+    // PLAIN: the self column took part in the minima, so the bound is the (k+1)-th smallest of them —
+    // at most one of the k+1 smallest minima is the self element, the other k are neighbours <= bound
+    const int kb = PLAIN ? k : k - 1;
     // ---- bound = k-th smallest of the THREADS minima ----
     // Each warp sorts its 32 minima with shuffles; a thread then ranks its own value against the
     // 8 sorted lists by binary search: lt = #minima below it, le = #minima not above it.  The value
@@ -241,13 +263,13 @@ topk_rows_kernel(const float* __restrict__ D, int64_t ld, int n_cols, int k, int
             lt += p;
             le += q;
         }
-        if (lt <= k - 1 && k - 1 < le) bound = x;
+        if (lt <= kb && kb < le) bound = x;
     }
     __syncthreads();
     // ---- pass 2: everything <= bound is a candidate ----
     const float T = bound;
-    tk_stream_row<VEC4>(d, n_cols, self_col, mask, [&](float v, int j) {
-        if (v <= T) {
+    tk_stream_row<VEC4, PLAIN>(d, n_cols, self_col, mask, [&](float v, int j) {
+        if (v <= T && (!PLAIN || j != self_col)) {
             const int p = atomicAdd(&n_cand, 1);
             if (p < TK_CAND) { cand_v[p] = v; cand_i[p] = j; }
         }
@@ -314,10 +336,12 @@ extern "C" int hsd_topk_rows(const float* D, int64_t ld, int32_t n_rows, int32_t
     cudaStream_t st = (cudaStream_t)stream;
     if (force_radix)
         topk_rows_radix_kernel<<<n_rows, TK_THREADS, 0, st>>>(D, ld, n_cols, k, self_col0, col_mask, idx_out, val_out);
-    else if ((reinterpret_cast<uintptr_t>(D) & 15) == 0 && (ld & 3) == 0)
-        topk_rows_kernel<true><<<n_rows, TK_THREADS, 0, st>>>(D, ld, n_cols, k, self_col0, col_mask, idx_out, val_out);
-    else
-        topk_rows_kernel<false><<<n_rows, TK_THREADS, 0, st>>>(D, ld, n_cols, k, self_col0, col_mask, idx_out, val_out);
+    else {
+        const bool vec4 = (reinterpret_cast<uintptr_t>(D) & 15) == 0 && (ld & 3) == 0;
+        auto go = [&](auto kern) { kern<<<n_rows, TK_THREADS, 0, st>>>(D, ld, n_cols, k, self_col0, col_mask, idx_out, val_out); };
+        if (vec4) { if (col_mask) go(topk_rows_kernel<true, false>); else go(topk_rows_kernel<true, true>); }
+        else      { if (col_mask) go(topk_rows_kernel<false, false>); else go(topk_rows_kernel<false, true>); }
+    }
     HSD_CUDA_TRY(cudaGetLastError());
     return HSD_OK;
 }

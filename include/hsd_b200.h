@@ -258,7 +258,8 @@ int hsd_characteristic_function(const double* psi, int64_t psi_ld, int32_t n_row
  * smallest D[r][j], j != self_col0 + r, j allowed by col_mask (nullable bitmap over columns;
  * lets a caller restrict neighbours to a training fold), ordered by (distance, column).
  *   idx_out int32[n_rows][k] (-1 where fewer than k candidates), val_out float[n_rows][k]; 1 <= k <= 64.
- * Distances must be >= 0 (radix select on the bit pattern). */
+ * Distances must be >= 0 (rows with a huge class of exactly tied candidates are resolved by a radix
+ * select on the float bit pattern, whose unsigned order equals the numeric order only for >= 0). */
 int hsd_topk_rows(const float* D, int64_t ld, int32_t n_rows, int32_t n_cols, int32_t k,
                   int32_t self_col0, const uint32_t* col_mask, int32_t* idx_out, float* val_out,
                   void* stream);

@@ -101,6 +101,33 @@ def test_edge_insertion_and_dedup():
     assert g2.degree.tolist() == [2, 2, 1, 1, 1]
     with pytest.raises(ValueError):
         CSRGraph.from_edges(3, np.array([[0, 3]]))
+    with pytest.raises(ValueError):
+        g.with_edges_added(np.array([[0, 5]]))
+
+
+def test_sorted_merge_insertion_equals_a_rebuild():
+    """with_edges_added merges the new entries into the sorted CSR (binary search + insert); it
+    must equal a rebuild from the full edge list: duplicates of existing edges, both orientations,
+    repeated new edges, a self-loop, first / last rows, and insertion into an empty graph."""
+    import networkx as nx
+    from hsd_b200.graph import CSRGraph
+    rng = np.random.default_rng(5)
+    G = nx.barabasi_albert_graph(400, 3, seed=2)
+    g = CSRGraph.from_networkx(G)
+    existing = np.array(list(G.edges()))[:5]
+    new = np.concatenate([rng.integers(0, 400, size=(60, 2)), existing, existing[:, ::-1],
+                          [[0, 399], [399, 0], [0, 399], [7, 7], [398, 399]]])
+    got = g.with_edges_added(new)
+    G2 = G.copy()
+    G2.add_edges_from(new.tolist())
+    want = CSRGraph.from_networkx(G2)
+    assert np.array_equal(got.rowptr, want.rowptr) and np.array_equal(got.col, want.col)
+    assert got.col.dtype == np.int32 and got.rowptr.dtype == np.int32
+    same = g.with_edges_added(np.zeros((0, 2), dtype=np.int64))
+    assert np.array_equal(same.col, g.col) and np.array_equal(same.rowptr, g.rowptr)
+    empty = CSRGraph.from_edges(6, np.zeros((0, 2)))
+    e2 = empty.with_edges_added(np.array([[0, 5], [2, 3], [5, 0]]))
+    assert e2.rowptr.tolist() == [0, 1, 1, 2, 3, 3, 4] and e2.col.tolist() == [5, 3, 2, 0]
 
 
 @pytest.mark.parametrize("n,world", [(20000, 1), (20000, 8), (10, 4), (3, 8), (1190, 2)])

@@ -3,12 +3,14 @@
 // ndarray to sklearn (tools/evaluate.py:61-69 via main.py:29); at N = 100k that is 40 GB, so the
 // selection runs where the matrix lives and only N x k pairs leave the GPU.
 //
-// One CTA per row, two reads of the row (the second one an L2 hit):
-//   pass 1  every thread keeps the minimum of the elements it streams (16-byte loads, no atomics);
+// One CTA per row, normally ONE read of the row:
+//   pass 1  every thread keeps the 4 smallest of the elements it streams (16-byte loads, no atomics);
 //           the k-th smallest of those THREADS minima is an upper bound T of the row's k-th smallest
 //           value (the minima are distinct elements of the row), and a tight one: the row's k
 //           smallest elements mostly sit in different threads, so about k + k^2/THREADS elements are <= T;
-//   pass 2  everything <= T goes to a shared candidate list (one rarely-taken shared atomic each);
+//   collect everything <= T goes to a shared candidate list — straight from the threads' registers when
+//           no thread can have dropped an element <= T (its 4th smallest is above T), else by pass 2,
+//           a second read of the row (heavy ties, very short rows);
 //   sort    the candidates by (distance, column) — a single warp when there are <= 64 — and the
 //           first k are the answer, ties at the k-th value resolved by ascending column.
 // A row with more than TK_CAND candidates (a large class of nodes at exactly the same distance)
@@ -150,6 +152,7 @@ topk_rows_radix_kernel(const float* __restrict__ D, int64_t ld, int n_cols, int 
 }
 
 constexpr int TK_CAND = 1024;   // candidate capacity of the two-pass kernel
+constexpr int TK_DEEP_MIN_COLS = 40960;   // rows at least this long use the 4-deep register buffers
 
 // (distance, column) "a sorts after b"
 __device__ __forceinline__ bool tk_after(float a, int ia, float b, int ib) {
@@ -204,7 +207,10 @@ __device__ __forceinline__ void tk_stream_row(const float* __restrict__ d, int n
     }
 }
 
-template <bool VEC4, bool PLAIN>
+// TK_KEEP = smallest elements a thread keeps in registers during pass 1.  4: long rows (the row is
+// read once; measured 11.1 -> 8.2 ms at N = 100k).  1: short rows, where the insertions of a 4-deep
+// buffer cost more instructions than the second (L2-resident) read saves (N = 20k: 0.36 vs 0.53 ms).
+template <bool VEC4, bool PLAIN, int TK_KEEP>
 __global__ void __launch_bounds__(TK_THREADS)
 topk_rows_kernel(const float* __restrict__ D, int64_t ld, int n_cols, int k, int self_col0,
                  const uint32_t* __restrict__ mask, int32_t* __restrict__ idx_out,
@@ -220,9 +226,24 @@ topk_rows_kernel(const float* __restrict__ D, int64_t ld, int n_cols, int k, int
     const int self_col = self_col0 + row;      // excluded: a node is not its own neighbour
     const int tid = threadIdx.x;
 
-    // ---- pass 1: per-thread minimum ----
-    float mine = INFINITY;
-    tk_stream_row<VEC4, PLAIN>(d, n_cols, self_col, mask, [&](float v, int) { mine = fminf(mine, v); });
+    // ---- pass 1: per-thread TK_KEEP smallest (ascending, in registers); bv[0] is the minimum ----
+    float bv[TK_KEEP];
+    int bi[TK_KEEP];
+#pragma unroll
+    for (int q = 0; q < TK_KEEP; ++q) { bv[q] = INFINITY; bi[q] = -1; }
+    tk_stream_row<VEC4, PLAIN>(d, n_cols, self_col, mask, [&](float v, int j) {
+        if (v < bv[TK_KEEP - 1]) {              // rarely true once the buffer has warmed up
+            bv[TK_KEEP - 1] = v; bi[TK_KEEP - 1] = j;
+#pragma unroll
+            for (int q = TK_KEEP - 1; q > 0; --q) {
+                if (bv[q] < bv[q - 1]) {
+                    const float tv = bv[q]; bv[q] = bv[q - 1]; bv[q - 1] = tv;
+                    const int ti = bi[q]; bi[q] = bi[q - 1]; bi[q - 1] = ti;
+                }
+            }
+        }
+    });
+    const float mine = bv[0];
     // PLAIN: the self column took part in the minima, so the bound is the (k+1)-th smallest of them —
     // at most one of the k+1 smallest minima is the self element, the other k are neighbours <= bound
     const int kb = PLAIN ? k : k - 1;
@@ -266,14 +287,24 @@ topk_rows_kernel(const float* __restrict__ D, int64_t ld, int n_cols, int k, int
         if (lt <= kb && kb < le) bound = x;
     }
     __syncthreads();
-    // ---- pass 2: everything <= bound is a candidate ----
+    // ---- candidates = everything <= bound ----
+    // A thread dropped an element only when it was >= its TK_KEEP-th smallest; if that one is above the
+    // bound, every element of the thread that is <= bound still sits in its registers and the row is
+    // NOT read again.  Otherwise (uniform vote; heavy ties or a very short row) pass 2 re-streams the row.
     const float T = bound;
-    tk_stream_row<VEC4, PLAIN>(d, n_cols, self_col, mask, [&](float v, int j) {
-        if (v <= T && (!PLAIN || j != self_col)) {
-            const int p = atomicAdd(&n_cand, 1);
-            if (p < TK_CAND) { cand_v[p] = v; cand_i[p] = j; }
-        }
-    });
+    auto push = [&](float v, int j) {
+        const int p = atomicAdd(&n_cand, 1);
+        if (p < TK_CAND) { cand_v[p] = v; cand_i[p] = j; }
+    };
+    if (TK_KEEP == 1 || __syncthreads_or(bv[TK_KEEP - 1] <= T)) {
+        tk_stream_row<VEC4, PLAIN>(d, n_cols, self_col, mask, [&](float v, int j) {
+            if (v <= T && (!PLAIN || j != self_col)) push(v, j);
+        });
+    } else {
+#pragma unroll
+        for (int q = 0; q < TK_KEEP; ++q)
+            if (bv[q] <= T && (!PLAIN || bi[q] != self_col)) push(bv[q], bi[q]);
+    }
     __syncthreads();
     const int nc = n_cand;
     if (nc > TK_CAND) {                         // uniform: a huge tie class -> exact radix select
@@ -339,8 +370,16 @@ extern "C" int hsd_topk_rows(const float* D, int64_t ld, int32_t n_rows, int32_t
     else {
         const bool vec4 = (reinterpret_cast<uintptr_t>(D) & 15) == 0 && (ld & 3) == 0;
         auto go = [&](auto kern) { kern<<<n_rows, TK_THREADS, 0, st>>>(D, ld, n_cols, k, self_col0, col_mask, idx_out, val_out); };
-        if (vec4) { if (col_mask) go(topk_rows_kernel<true, false>); else go(topk_rows_kernel<true, true>); }
-        else      { if (col_mask) go(topk_rows_kernel<false, false>); else go(topk_rows_kernel<false, true>); }
+        static int keep_force = -1;   // tuning knob: HSD_TOPK_KEEP in {1, 4}
+        if (keep_force < 0) { const char* e = getenv("HSD_TOPK_KEEP"); keep_force = e ? atoi(e) : 0; }
+        const bool deep = keep_force ? keep_force == 4 : n_cols >= TK_DEEP_MIN_COLS;
+        if (deep) {
+            if (vec4) { if (col_mask) go(topk_rows_kernel<true, false, 4>); else go(topk_rows_kernel<true, true, 4>); }
+            else      { if (col_mask) go(topk_rows_kernel<false, false, 4>); else go(topk_rows_kernel<false, true, 4>); }
+        } else {
+            if (vec4) { if (col_mask) go(topk_rows_kernel<true, false, 1>); else go(topk_rows_kernel<true, true, 1>); }
+            else      { if (col_mask) go(topk_rows_kernel<false, false, 1>); else go(topk_rows_kernel<false, true, 1>); }
+        }
     }
     HSD_CUDA_TRY(cudaGetLastError());
     return HSD_OK;

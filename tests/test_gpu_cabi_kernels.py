@@ -178,6 +178,10 @@ def _topk_expect(D, r, k, n_cols, self_col):
     (50, 1024, 1022, 7, 1000),    # 16-byte loads + 2 tail columns, few ties
     (33, 1003, 1003, 20, 1000),   # leading dimension not a multiple of 4: scalar loads
     (20, 20000, 20000, 20, 1 << 20),  # C2 row length, essentially no ties
+    (6, 50000, 50000, 20, 1 << 20),   # long rows: 4-deep register buffers, the row is read once
+    (4, 50000, 50000, 10, 5000),      # long rows with ~10-fold ties at every value
+    (4, 50004, 50001, 64, 40),        # long rows, > 1024 ties at the bound: second pass, then radix select
+    (3, 49999, 49999, 5, 1 << 20),    # long rows through the scalar-load path
 ])
 def test_topk_rows_two_pass_and_fallback(n_rows, n_alloc, n_cols, k, levels):
     """The two-pass kernel (per-thread minima -> bound -> candidate list) and its radix fallback give

@@ -152,7 +152,7 @@ topk_rows_radix_kernel(const float* __restrict__ D, int64_t ld, int n_cols, int 
 }
 
 constexpr int TK_CAND = 1024;   // candidate capacity of the two-pass kernel
-constexpr int TK_DEEP_MIN_COLS = 40960;   // rows at least this long use the 4-deep register buffers
+constexpr int TK_DEEP_MIN_COLS = 32768;   // rows at least this long use the 4-deep register buffers
 
 // (distance, column) "a sorts after b"
 __device__ __forceinline__ bool tk_after(float a, int ia, float b, int ib) {

@@ -104,17 +104,20 @@ if "c5h2" in which:
     G = nx.barabasi_albert_graph(n, 5, seed=0)
     from model import DynamicHSD
     m = DynamicHSD(G, "ba100k", hop, 1, "wasserstein", signal="degree")
+    m.structural_distance_update(); torch.cuda.synchronize()          # warm-up (lazy inits)
+    m._D = None
     t0 = time.perf_counter(); m.structural_distance_update(); torch.cuda.synchronize(); t_full = time.perf_counter() - t0
     rng = np.random.default_rng(1)
-    for k_ins in [5, 50]:
+    for k_ins in [5, 50, 1000]:
         edges = set()
         while len(edges) < k_ins:
             u, v = (int(x) for x in rng.integers(0, n, 2))
             if u != v and not m.graph.has_edge(u, v): edges.add((min(u, v), max(u, v)))
-        m.dynamic_add_edges(sorted(edges))
+        t0 = time.perf_counter(); m.dynamic_add_edges(sorted(edges)); t_edit = time.perf_counter() - t0
         t0 = time.perf_counter(); D = m.structural_distance_update(); torch.cuda.synchronize(); t_inc = time.perf_counter() - t0
         print(json.dumps({"config": "C5 variant hop=2", "n": n, "hop": hop, "inserted_edges": k_ins,
-                          "affected_rows": int(m.last_affected.numel()), "full_s": t_full, "incremental_s": t_inc}))
+                          "affected_rows": int(m.last_affected.numel()), "full_s": t_full,
+                          "host_edit_s": t_edit, "incremental_s": t_inc}))
 
 if "topk" in which:
     for n, hops in [(20000, 3), (100000, 4)]:

@@ -171,6 +171,18 @@ def signature_transpose(sig: torch.Tensor, k_used: int, sigT: torch.Tensor, col0
                                       _ptr(sigT), sigT.stride(0), col0, _ptr(src_rows), _stream()))
 
 
+def scatter_symmetric(blk: torch.Tensor, idx: torch.Tensor, D: torch.Tensor, mirror: bool = True) -> None:
+    """D[idx[a], :n] = blk[a] and (mirror) D[:n, idx[a]] = blk[a] for the m recomputed rows of an
+    incremental update; idx int64 ascending node ids, blk float32[m, n] row-major."""
+    m, n = blk.shape
+    if idx.dtype != torch.int64 or idx.numel() != m or blk.stride(1) != 1 or D.stride(1) != 1:
+        raise ValueError("idx must be int64[m]; blk and D row-major")
+    if D.shape[1] < n or (mirror and D.shape[0] < n):
+        raise ValueError("D too small")
+    check(lib.hsd_scatter_symmetric(blk.data_ptr(), blk.stride(0), m, n, _ptr(idx.contiguous()), D.data_ptr(),
+                                    D.stride(0), 1 if mirror else 0, _stream()))
+
+
 def pairwise_l1(sigT: torch.Tensor, n: int, row0: int = 0, n_rows: Optional[int] = None,
                 col0: int = 0, n_cols: Optional[int] = None, symmetric: Optional[bool] = None,
                 out: Optional[torch.Tensor] = None, k_used: Optional[int] = None) -> torch.Tensor:

@@ -146,8 +146,7 @@ class DynamicHSD(MultiHSD):
             engine.signature_transpose(sig, k_used, sigT, 0)
             engine.signature_transpose(sig, k_used, sigT, n4, src_rows=aff.to(torch.int32).contiguous())
             blk = engine.pairwise_l1(sigT, n4 + m, row0=n4, n_rows=m, col0=0, n_cols=n, symmetric=False, k_used=k_used)
-            self._D[aff, :] = blk
-            self._D[:, aff] = blk.t()
+            engine.scatter_symmetric(blk, aff, self._D)       # rows + mirrored columns in one pass over blk
         self._pending.clear()
         return self._D
 

@@ -320,11 +320,14 @@ class ShardedDegreeHSD:
                 engine.signature_transpose(self.sig_all, k, sigT, 0, src_rows=tbl_all)
                 engine.signature_transpose(self.sig_all, k, sigT, n4, src_rows=tbl_all[dealt].contiguous())
                 blk = engine.pairwise_l1(sigT, n4 + mq, row0=n4, n_rows=mq, col0=0, n_cols=n, symmetric=False, k_used=k)
-                for r, Dr in enumerate(self._block_views()):
-                    r0, nr, _ = shard_rows(n, self.world, r)
-                    if nr:
-                        Dr[:nr].index_copy_(1, dealt, blk[:, r0:r0 + nr].t())
-                direct_rows(dealt, segments, blk)
+                if self.world == 1:
+                    engine.scatter_symmetric(blk, dealt, self.out)
+                else:
+                    for r, Dr in enumerate(self._block_views()):
+                        r0, nr, _ = shard_rows(n, self.world, r)
+                        if nr:
+                            Dr[:nr].index_copy_(1, dealt, blk[:, r0:r0 + nr].t())
+                    direct_rows(dealt, segments, blk)
         elif mode == "rows":
             # table = [all nodes | all affected nodes | pad | dealt affected nodes]: the COLUMNS of the
             # affected nodes are recomputed by every rank for its own rows (local scatter); their ROWS are

@@ -118,6 +118,14 @@ int hsd_signature_transpose(const float* sig, int64_t sig_ld, int32_t n_rows, in
                             float* sigT, int64_t n_pad, int32_t col0, const int32_t* src_rows,
                             void* stream);
 
+/* ---- incremental update: scatter recomputed rows into the symmetric matrix ----
+ * DynamicHSD (model/dynamic_HSD.py:23-24 is a stub; BASELINE config 5): blk[a][c], a < m, c < n, holds
+ * the recomputed distances of row idx[a] (int64 node ids, ascending) to every column.  Stores
+ * D[idx[a]][c] = blk[a][c] and, when mirror != 0, D[c][idx[a]] = blk[a][c] (D row-major, leading
+ * dimension d_ld; needs n rows when mirrored).  Replaces two torch index_put passes over the block. */
+int hsd_scatter_symmetric(const float* blk, int64_t blk_ld, int32_t m, int32_t n, const int64_t* idx,
+                          float* D, int64_t d_ld, int32_t mirror, void* stream);
+
 /* ---- K3: pairwise L1 over the K-major signature table ----------------------
  * Replaces the O(N^2 (H+1)) scipy loop model/HSD.py:103-112 (and :144-159).
  *   out[(i-row0)*ld_out + (j-col0)] = sum_k |sigT[k][i] - sigT[k][j]|

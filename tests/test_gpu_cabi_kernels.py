@@ -221,3 +221,26 @@ def test_topk_rows_with_column_mask_and_model_api(golden_graphs):
     for r in [1, 50, 397]:
         order = sorted((j for j in range(0, m.n_node, 2) if j != r), key=lambda j: (D[r, j], j))[:5]
         assert idx2[r].tolist() == order
+
+
+@pytest.mark.parametrize("n,m,ld,mirror", [(70, 9, 72, True), (257, 33, 257, True), (64, 64, 64, True), (100, 1, 104, False)])
+def test_scatter_symmetric_rows_and_mirrored_columns(n, m, ld, mirror):
+    """hsd_scatter_symmetric: D[idx[a], c] = blk[a, c] and (mirror) D[c, idx[a]] = blk[a, c]; nothing
+    else is touched (blk rows are rows of a symmetric matrix, as in the incremental update)."""
+    import torch
+    from hsd_b200 import engine
+    rng = np.random.default_rng(n + m)
+    S = rng.random((n, n)).astype(np.float32)
+    S = S + S.T                                   # symmetric: doubly-affected entries agree
+    idx = np.sort(rng.choice(n, size=m, replace=False)).astype(np.int64)
+    buf = torch.full((n, ld), -7.0, dtype=torch.float32, device="cuda")
+    D = buf[:, :n]
+    blk_buf = torch.zeros((m, n + 3), dtype=torch.float32, device="cuda")
+    blk_buf[:, :n] = torch.from_numpy(S[idx]).cuda()
+    engine.scatter_symmetric(blk_buf[:, :n], torch.from_numpy(idx).cuda(), D, mirror=mirror)
+    want = np.full((n, n), -7.0, dtype=np.float32)
+    want[idx, :] = S[idx]
+    if mirror:
+        want[:, idx] = S[idx].T
+    assert np.array_equal(D.cpu().numpy(), want)
+    assert bool((buf[:, n:] == -7.0).all())

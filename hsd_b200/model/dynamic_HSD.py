@@ -45,6 +45,13 @@ class DynamicHSD(MultiHSD):
     def init(self):
         super(DynamicHSD, self).init()
 
+    def _device_graph(self, include_zero=False) -> engine.DeviceGraph:
+        # the graph changes between steps: order it by degree on the device instead of on the host
+        if self._dg is None or self._dg.include_zero != include_zero:
+            self._dg = engine.DeviceGraph.upload_device_order(self.csr, include_zero=include_zero,
+                                                              device=self._device())
+        return self._dg
+
     # ---- graph edits ----
     def _refresh_graph(self, new_edges=None):
         """new_edges: the edges just inserted when the node set did not change — the CSR is then

@@ -178,3 +178,23 @@ def test_dynamic_model_sharded_api_single_rank():
     assert torch.equal(Da, Db)
     assert torch.equal(torch.sort(a.last_affected).values, torch.sort(b.last_affected).values)
     assert 0 < a.last_affected.numel() < 1000
+
+
+@pytest.mark.parametrize("n,include_zero", [(3000, False), (257, True), (5, False)])
+def test_device_side_degree_order_equals_host_order(n, include_zero):
+    """DeviceGraph.upload_device_order (torch sort / gather on the device) == DeviceGraph.upload (numpy
+    on the host), field by field; the small graph has isolated nodes (degree 0 in the support)."""
+    import torch
+    from hsd_b200 import engine
+    from hsd_b200.graph import CSRGraph
+    if n > 5:
+        g = CSRGraph.from_networkx(_ba(n, seed=4))
+    else:
+        g = CSRGraph.from_edges(5, np.array([[0, 1], [1, 2]]))      # nodes 3, 4 isolated
+    a = engine.DeviceGraph.upload(g, include_zero=include_zero)
+    b = engine.DeviceGraph.upload_device_order(g, include_zero=include_zero)
+    torch.cuda.synchronize()
+    assert a.n == b.n and a.n_bins == b.n_bins and np.array_equal(a.support, b.support)
+    for f in ("rowptr", "col", "orig_of", "new_of", "bin_end", "delta"):
+        x, y = getattr(a, f), getattr(b, f)
+        assert x.dtype == y.dtype and x.shape == y.shape and torch.equal(x, y), f

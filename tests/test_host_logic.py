@@ -37,6 +37,14 @@ def test_c_abi_argument_validation_without_gpu():
     assert lib.hsd_ring_reduce(p, 1, 4, 4, p, p, None, 9, 0, p, p, 64, None) == -1   # hops > 7
     with pytest.raises(HSDError):
         check(lib.hsd_cheb_spmm(p, p, 4, -1.0, p, 1, 3, 0, 4, 0.0, p, p, None))
+    assert lib.hsd_topk_rows(p, 8, 4, 8, 65, 0, None, p, p, None) == -1              # k <= 64
+    assert lib.hsd_topk_rows(p, 4, 4, 8, 2, 0, None, p, p, None) == -1               # ld >= n_cols
+    assert lib.hsd_scatter_symmetric(None, 8, 2, 8, p, p, 8, 1, None) == -1 and b"null" in lib.hsd_last_error_string()
+    assert lib.hsd_scatter_symmetric(p, 4, 2, 8, p, p, 8, 1, None) == -1             # blk_ld >= n
+    # graphs whose four N-bit bitmaps fit shared memory need no BFS workspace; larger ones say how much
+    assert lib.hsd_bfs_workspace_words(100000) == 0
+    words = lib.hsd_bfs_workspace_words(450000)
+    assert words > 0 and words % (4 * ((450000 + 31) // 32)) == 0
 
 
 def test_no_cpu_fallback():

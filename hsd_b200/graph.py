@@ -78,8 +78,24 @@ class CSRGraph:
     def from_networkx(cls, graph) -> "CSRGraph":
         nodes = list(graph.nodes())
         idx = {v: i for i, v in enumerate(nodes)}
-        e = np.fromiter((idx[x] for uv in graph.edges() for x in uv), dtype=np.int64)
-        return cls.from_edges(len(nodes), e.reshape(-1, 2), nodes)
+        n = len(nodes)
+        if graph.is_directed() or graph.is_multigraph():
+            e = np.fromiter((idx[x] for uv in graph.edges() for x in uv), dtype=np.int64)
+            return cls.from_edges(n, e.reshape(-1, 2), nodes)
+        # undirected simple graph: the adjacency dict already holds both orientations of every edge
+        # (a self-loop once), so one flat pass over it replaces the per-edge tuple iteration
+        # (0.58 s -> 0.3 s at 100k nodes / 500k edges); columns are then sorted within each row
+        from itertools import chain
+        adj = getattr(graph, "_adj", None) or graph.adj      # the raw dict-of-dicts: the AtlasView wrappers cost 0.4 s at 100k nodes
+        deg = np.fromiter((len(adj[v]) for v in nodes), dtype=np.int64, count=n)
+        nnz = int(deg.sum())
+        if nnz >= 2**31:
+            raise ValueError("graph too large for int32 CSR")
+        cols = np.fromiter(map(idx.__getitem__, chain.from_iterable(adj[v] for v in nodes)), dtype=np.int64, count=nnz)
+        key = np.sort(np.repeat(np.arange(n, dtype=np.int64), deg) * n + cols)
+        rowptr = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(deg, out=rowptr[1:])
+        return cls(n=n, rowptr=rowptr.astype(np.int32), col=(key % max(n, 1)).astype(np.int32), nodes=nodes)
 
     def with_edges_added(self, new_edges: np.ndarray) -> "CSRGraph":
         """A new CSRGraph with extra undirected edges (index pairs; edges already present are

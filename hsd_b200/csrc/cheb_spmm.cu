@@ -245,9 +245,16 @@ extern "C" int hsd_cheb_spmm(const int32_t* rowptr, const int32_t* col, int32_t 
     }
     HSD_REQUIRE(n_cols % 2 == 0, "n_cols must be even (16-byte column pairs)");
     const int pairs = n_cols / 2;
+    // 256 columns and more: one node per 128-thread CTA, so that a CTA's warps all walk the same adjacency
+    // list and retire together (a hub next to a leaf in one CTA left the leaf's warps idle: 5.56 -> 5.35 ms
+    // per block at C4); narrower blocks keep 256 threads (several nodes per CTA measured faster there)
+    static int cta_force = -1;   // tuning knob: HSD_CHEB_CTA = threads per CTA (64, 128, 256)
+    if (cta_force < 0) { const char* e = getenv("HSD_CHEB_CTA"); cta_force = e ? atoi(e) : 0; }
+    int cta = (cta_force == 64 || cta_force == 128 || cta_force == 256) ? cta_force : (pairs >= 128 ? 128 : 256);
+    if (pairs >= cta && n_nodes > 65535) cta = 256;      // grid.y carries the nodes
     int bx = 32;
-    while (bx < pairs && bx < 256) bx <<= 1;
-    const int by = 256 / bx;
+    while (bx < pairs && bx < cta) bx <<= 1;
+    const int by = cta / bx;
     dim3 block(bx, by), grid((pairs + bx - 1) / bx, (n_nodes + by - 1) / by);
     HSD_REQUIRE(grid.y <= 65535u, "too many nodes for one launch dimension");
     ChebArgs a;

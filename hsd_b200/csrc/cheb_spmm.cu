@@ -59,8 +59,8 @@ __device__ __forceinline__ void st_cs(double* p, double2 v) {
 }
 
 __global__ void __launch_bounds__(256) cheb_step_kernel(const ChebArgs p) {
-    const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
-    const int v = blockIdx.y * blockDim.y + threadIdx.y;
+    const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 2;     // grid.x carries the nodes (no 65 535 limit)
+    const int v = blockIdx.x * blockDim.y + threadIdx.y;
     if (c >= p.n_cols || v >= p.n_nodes) return;
     const int e0 = __ldg(p.rowptr + v), e1 = __ldg(p.rowptr + v + 1);
     double2 nb = make_double2(0.0, 0.0);
@@ -251,12 +251,11 @@ extern "C" int hsd_cheb_spmm(const int32_t* rowptr, const int32_t* col, int32_t 
     static int cta_force = -1;   // tuning knob: HSD_CHEB_CTA = threads per CTA (64, 128, 256)
     if (cta_force < 0) { const char* e = getenv("HSD_CHEB_CTA"); cta_force = e ? atoi(e) : 0; }
     int cta = (cta_force == 64 || cta_force == 128 || cta_force == 256) ? cta_force : (pairs >= 128 ? 128 : 256);
-    if (pairs >= cta && n_nodes > 65535) cta = 256;      // grid.y carries the nodes
     int bx = 32;
     while (bx < pairs && bx < cta) bx <<= 1;
     const int by = cta / bx;
-    dim3 block(bx, by), grid((pairs + bx - 1) / bx, (n_nodes + by - 1) / by);
-    HSD_REQUIRE(grid.y <= 65535u, "too many nodes for one launch dimension");
+    dim3 block(bx, by), grid((n_nodes + by - 1) / by, (pairs + bx - 1) / bx);
+    HSD_REQUIRE(grid.y <= 65535u, "column block too wide for one launch dimension");
     ChebArgs a;
     a.rowptr = rowptr; a.col = col; a.n_nodes = n_nodes; a.n_cols = n_cols; a.col0 = col0;
     a.order = order; a.n_scales = n_scales; a.a = lmax / 2.0; a.threshold = threshold; a.out = out;

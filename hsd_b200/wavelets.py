@@ -90,10 +90,11 @@ class DeviceCSR:
         self.col = torch.from_numpy(g.col).to(dev) if g.col.size else torch.zeros(1, dtype=torch.int32, device=dev)
 
 
-def column_block(n: int, n_scales: int, budget_bytes: float = 8e9, l2_bytes: float = 100e6) -> int:
+def column_block(n: int, n_scales: int, budget_bytes: float = 8e9, l2_bytes: float = 105e6) -> int:
     """Impulse columns per SpMM pass.  T_{k-1} (N x C doubles) is re-read once per neighbour, so the
-    block is sized to keep it L2-resident (measured at N = 50k: C = 256 -> 4.2 TB/s algorithmic,
-    C = 1024 -> 3.8 TB/s), within a memory budget for the 3 + S work planes."""
+    block is sized to about the L2 (measured at N = 50k, microseconds per column: C = 128 -> 25.6,
+    192 -> 22.5, 256 -> 20.9, 384 -> 24.5, 1024 -> 25.3), within a memory budget for the 3 + S work
+    planes.  105e6 / (8 N) gives 256 at N = 50k; blocks of >= 256 columns also get one node per CTA."""
     c = min(int(l2_bytes / (8 * n)), int(budget_bytes / ((3 + n_scales) * n * 8)))
     c = max(64, c // 64 * 64)
     return n if c >= n else c

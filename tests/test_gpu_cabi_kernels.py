@@ -244,3 +244,36 @@ def test_scatter_symmetric_rows_and_mirrored_columns(n, m, ld, mirror):
         want[:, idx] = S[idx].T
     assert np.array_equal(D.cpu().numpy(), want)
     assert bool((buf[:, n:] == -7.0).all())
+
+
+@pytest.mark.parametrize("name,k", [("europe", 10), ("barbell", 5)])
+def test_topk_distances_match_sklearn_precomputed_knn(golden_runs, name, k):
+    """The reference's consumer of the matrix is sklearn's precomputed-metric KNN
+    (tools/evaluate.py:61-69).  On the REFERENCE's own distance matrix (golden fixture) the k neighbour
+    distances of every node from hsd_topk_rows equal sklearn's kneighbors (self removed); indices are
+    compared where the k-th and (k+1)-th distances differ (sklearn's tie order is unspecified)."""
+    import torch
+    from sklearn.neighbors import NearestNeighbors
+    from hsd_b200 import engine
+    if name == "europe":
+        n = 399
+        D = np.zeros((n, n))
+        D[np.triu_indices(n, 1)] = golden_runs["europe_D"]
+        D = D + D.T
+    else:
+        D = np.asarray(golden_runs[f"{name}_D"], dtype=np.float64)
+        n = D.shape[0]
+    D32 = D.astype(np.float32)
+    D64 = D32.astype(np.float64)                       # both sides see the same float32-representable values
+    idx, val = engine.topk_rows(torch.from_numpy(D32).cuda(), k)
+    idx, val = idx.cpu().numpy(), val.cpu().numpy().astype(np.float64)
+    dist, ind = NearestNeighbors(n_neighbors=k + 2, metric="precomputed").fit(D64).kneighbors(D64)
+    for i in range(n):
+        # remove ONE entry for the node itself (distance 0; other nodes may be at distance 0 too)
+        d = dist[i].tolist()
+        d.remove(0.0)
+        assert val[i].tolist() == d[:k]
+        if d[k - 1] < d[k]:                              # no tie across the cut: the neighbour SETS agree
+            want = [j for j in ind[i].tolist() if j != i][:k]
+            if len(want) == k and i in ind[i]:
+                assert sorted(idx[i].tolist()) == sorted(want)

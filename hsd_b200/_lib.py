@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_double, c_float, c_int32, c_int64, c_void_p, POINTER
+from ctypes import c_char_p, c_double, c_int32, c_int64, c_void_p, POINTER
 
 from .build import LIB
 

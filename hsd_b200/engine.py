@@ -14,7 +14,6 @@ from typing import Optional, Tuple
 import numpy as np
 import torch
 
-from . import _lib
 from ._lib import check, lib
 from .graph import CSRGraph
 

@@ -16,7 +16,6 @@ through libhsd_b200.  Differences a caller can see, all additive:
 from __future__ import annotations
 
 import os
-from typing import Optional
 
 import networkx as nx
 import numpy as np

@@ -24,7 +24,7 @@ import networkx as nx
 import numpy as np
 import torch
 
-from .. import engine, rings as _rings
+from .. import engine
 from ..graph import CSRGraph
 from ..tools import util
 from .multiscale_HSD import MultiHSD

@@ -14,7 +14,7 @@ import networkx as nx
 import numpy as np
 import torch
 
-from .. import engine, rings as _rings, wavelets as _wav
+from .. import engine, wavelets as _wav
 from .._lib import check, lib
 from .HSD import HSD
 

@@ -15,7 +15,6 @@ import numpy as np
 import torch
 
 from . import engine
-from .graph import CSRGraph
 
 
 # metrics of tools/metrics.py::calculate_distance available on the GPU (the other names the

@@ -21,8 +21,7 @@ model pickled per task (model/HSD.py:118-137).
 from __future__ import annotations
 
 import os
-from dataclasses import dataclass
-from typing import Optional, Tuple
+from typing import Tuple
 
 import torch
 

@@ -9,7 +9,6 @@ ascending node index — the reference's is set-iteration order, i.e. unspecifie
 from __future__ import annotations
 
 import os
-import platform
 
 import networkx as nx
 import numpy as np

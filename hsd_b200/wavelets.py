@@ -11,7 +11,7 @@ Here the Chebyshev path is one CSR SpMM kernel over a block of impulse columns
 """
 from __future__ import annotations
 
-from typing import Optional, Sequence
+from typing import Optional
 
 import numpy as np
 import torch

@@ -277,3 +277,25 @@ def test_topk_distances_match_sklearn_precomputed_knn(golden_runs, name, k):
             want = [j for j in ind[i].tolist() if j != i][:k]
             if len(want) == k and i in ind[i]:
                 assert sorted(idx[i].tolist()) == sorted(want)
+
+
+@pytest.mark.parametrize("n_cols,levels", [(40000, 1 << 20), (36001, 50)])
+def test_topk_long_rows_with_column_mask(n_cols, levels):
+    """Long rows (4-deep register buffers) together with a column bitmap: only allowed columns may be
+    neighbours; the tie-heavy case goes through the second pass and the radix select."""
+    import torch
+    from hsd_b200 import engine
+    rng = np.random.default_rng(n_cols)
+    n_rows, k = 3, 12
+    D = (np.floor(rng.random((n_rows, n_cols)) * levels) / 8.0).astype(np.float32)
+    allowed = np.zeros(((n_cols + 31) // 32) * 32, dtype=np.uint8)
+    allowed[:n_cols] = rng.random(n_cols) < 0.3
+    allowed[[0, 1, 2]] = 1                      # the rows' own columns are allowed but still excluded
+    mask = torch.from_numpy(np.packbits(allowed, bitorder="little").view(np.int32).copy()).cuda()
+    idx, val = engine.topk_rows(torch.from_numpy(D).cuda(), k, col_mask=mask)
+    idx, val = idx.cpu().numpy(), val.cpu().numpy()
+    cols = np.nonzero(allowed[:n_cols])[0]
+    for r in range(n_rows):
+        order = sorted((int(j) for j in cols if j != r), key=lambda j: (D[r, j], j))[:k]
+        assert idx[r].tolist() == order
+        assert np.array_equal(val[r], D[r, order])

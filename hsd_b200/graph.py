@@ -91,7 +91,11 @@ class CSRGraph:
         nnz = int(deg.sum())
         if nnz >= 2**31:
             raise ValueError("graph too large for int32 CSR")
-        cols = np.fromiter(map(idx.__getitem__, chain.from_iterable(adj[v] for v in nodes)), dtype=np.int64, count=nnz)
+        flat = chain.from_iterable(adj[v] for v in nodes)
+        if n and type(nodes[0]) is int and type(nodes[-1]) is int and nodes == list(range(n)):
+            cols = np.fromiter(flat, dtype=np.int64, count=nnz)     # labels are the indices already
+        else:
+            cols = np.fromiter(map(idx.__getitem__, flat), dtype=np.int64, count=nnz)
         key = np.sort(np.repeat(np.arange(n, dtype=np.int64), deg) * n + cols)
         rowptr = np.zeros(n + 1, dtype=np.int64)
         np.cumsum(deg, out=rowptr[1:])
@@ -140,6 +144,14 @@ class CSRGraph:
 
     def neighbors(self, i: int) -> np.ndarray:
         return self.col[self.rowptr[i]:self.rowptr[i + 1]]
+
+
+def has_nonunit_weights(graph) -> bool:
+    """True if some edge of a networkx graph carries a 'weight' other than 1.  Edges without any
+    attribute (every edge list the reference ships) are skipped with one truthiness test of their
+    attribute dict, so the scan costs ~0.05 s at 1e6 adjacency entries instead of 0.5 s."""
+    adj = getattr(graph, "_adj", None) or graph.adj
+    return any(d.get("weight", 1.0) != 1.0 for nbrs in adj.values() for d in nbrs.values() if d)
 
 
 def powerlaw_graph(n: int, m: int = 5, seed: int = 0) -> CSRGraph:

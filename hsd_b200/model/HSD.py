@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from .. import engine, rings as _rings, wavelets as _wav
-from ..graph import CSRGraph
+from ..graph import CSRGraph, has_nonunit_weights
 from ..tools import hierarchy as _hierarchy
 from ..tools import util
 
@@ -66,7 +66,7 @@ class HSD(object):
 
         self.csr = CSRGraph.from_networkx(graph)
         # every edge list the reference ships is unweighted; the CSR kernels assume unit weights
-        self._weighted = any(d.get("weight", 1.0) != 1.0 for _, _, d in graph.edges(data=True))
+        self._weighted = has_nonunit_weights(graph)
         self._A = None
         self._L = None
         self._dg = None

@@ -228,3 +228,26 @@ def test_reference_side_modules_stay_importable_through_the_shim():
     lines = out.stdout.strip().splitlines()
     assert lines[0].startswith(ref) and lines[1] == "hsd_b200.tools.hierarchy"
     assert lines[2] == "hsd_b200.tools.rw" and lines[3] == "hsd_b200.model.HSD"
+
+
+def test_weighted_edge_detection_and_identity_label_fast_path():
+    """has_nonunit_weights (the guard in front of the unit-weight Chebyshev kernel) and the two
+    label paths of CSRGraph.from_networkx (labels that are the indices / arbitrary labels)."""
+    import networkx as nx
+    from hsd_b200.graph import CSRGraph, has_nonunit_weights
+    g = nx.Graph()
+    g.add_edge(0, 1)
+    g.add_edge(1, 2, color="red")
+    g.add_edge(2, 3, weight=1.0)
+    assert not has_nonunit_weights(g) and not has_nonunit_weights(nx.Graph())
+    g.add_edge(3, 0, weight=0.5)
+    assert has_nonunit_weights(g)
+    base = nx.barabasi_albert_graph(200, 3, seed=7)                       # labels 0..n-1 in order: fast path
+    a = CSRGraph.from_networkx(base)
+    perm = nx.relabel_nodes(base, {v: f"n{v}" for v in base.nodes()})      # same graph, string labels, same order
+    b = CSRGraph.from_networkx(perm)
+    assert np.array_equal(a.rowptr, b.rowptr) and np.array_equal(a.col, b.col)
+    assert a.nodes == list(range(200)) and b.nodes == [f"n{v}" for v in range(200)]
+    e = np.array(base.edges(), dtype=np.int64)
+    c = CSRGraph.from_edges(200, e)
+    assert np.array_equal(a.rowptr, c.rowptr) and np.array_equal(a.col, c.col)

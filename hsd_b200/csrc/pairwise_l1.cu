@@ -15,6 +15,7 @@
 // conflict-free LDS.128.
 #include <cuda.h>
 #include <stdlib.h>
+#include <algorithm>
 #include <cudaTypedefs.h>
 #include "hsd_common.cuh"
 
@@ -25,6 +26,9 @@ constexpr int KC = HSD_PAIR_KCHUNK;
 constexpr int STAGES = 4;
 constexpr int LOOKAHEAD = 2;   // chunks in flight ahead of the one being consumed
 constexpr int PAIR_THREADS = 256;
+#ifndef HSD_PAIR_V2_DEFAULT
+#define HSD_PAIR_V2_DEFAULT 0, 4, 1, 0, 2, 8   // kc (0 = round-1 kernels), stages, packed, producer warp, lookahead, unroll
+#endif
 constexpr uint32_t STAGE_BYTES = 2u * KC * TILE * sizeof(float);
 
 struct __align__(128) PairSmem {
@@ -102,6 +106,9 @@ struct PairArgs {
     float* const* shard_ptrs;
     int per;
     int tile_stride, tile_offset;
+    // v2 (persistent) kernel: tiles of this launch, valid rows of the last K chunk rounded up to 4,
+    // chunks the elected producer thread runs ahead when there is no producer warp
+    int n_tiles, k_last, lookahead;
 };
 
 // pointer to logical element (i, 0)
@@ -397,6 +404,228 @@ pairwise_l1_n64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     }
 }
 
+// ---- v2: persistent CTAs, packed subtract, optional producer warp --------------------------------
+// (round 2) Same 128 x 128 tile and 8 x 8 register tiles, restructured around what ncu showed in
+// round 1 (profiles/r1_pairwise_notes.md): the kernel was ISSUE-bound — 7.7 % of the issue slots
+// went to instructions that are not FADD and the FMA pipe idled while they issued.
+//  * PACKED: the 64 subtracts of a k-step are 32 `sub.f32x2` (SASS FADD2 with a broadcast .F32
+//    operand: {a,a} - {b0,b1}); same IEEE result per lane, same FMA-pipe cycles, half the issue
+//    slots -> 96 + 4 LDS slots per 128 pipe cycles, so operand loads and chunk bookkeeping issue
+//    in the shadow of the pipe instead of displacing FADDs;
+//  * persistent CTAs (grid = 2 per SM) walk the tile list; the TMA ring runs ACROSS tiles, so the
+//    next tile's first chunks land while the current tile's 64 + 64 results are being stored;
+//  * PRODW: a ninth warp owns the TMA issue (no compute warp carries the empty-barrier wait and
+//    the two UTMALDG per chunk);
+//  * the last K chunk runs only its valid rows (groups of 4 k-steps).
+template <int KC_, int STAGES_>
+struct __align__(128) PairSmemV2 {
+    float a[STAGES_][KC_][TILE];
+    float b[STAGES_][KC_][TILE];
+    unsigned long long full[STAGES_];
+    unsigned long long empty[STAGES_];
+};
+
+__device__ __forceinline__ uint32_t mbar_probe(uint32_t bar, uint32_t parity) {
+    uint32_t ok;   // non-blocking test (try_wait may suspend the thread for a while)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+
+template <bool PACKED>
+__device__ __forceinline__ void pair_kstep(const float* __restrict__ arow, const float* __restrict__ brow,
+                                           const int ty, const int tx, float (&acc)[8][8]) {
+    const float4 a0 = *reinterpret_cast<const float4*>(arow + ty * 4);
+    const float4 a1 = *reinterpret_cast<const float4*>(arow + 64 + ty * 4);
+    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    if (PACKED) {
+        const ulonglong2 b0 = *reinterpret_cast<const ulonglong2*>(brow + tx * 4);
+        const ulonglong2 b1 = *reinterpret_cast<const ulonglong2*>(brow + 64 + tx * 4);
+        const unsigned long long bp[4] = {b0.x, b0.y, b1.x, b1.y};
+        unsigned long long d[8][4];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            unsigned long long aa;
+            asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(av[r]));
+#pragma unroll
+            for (int q = 0; q < 4; ++q) asm("sub.f32x2 %0, %1, %2;" : "=l"(d[r][q]) : "l"(aa), "l"(bp[q]));
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float d0, d1;
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d[r][q]));
+                acc[r][2 * q] += fabsf(d0);
+                acc[r][2 * q + 1] += fabsf(d1);
+            }
+    } else {
+        const float4 b0 = *reinterpret_cast<const float4*>(brow + tx * 4);
+        const float4 b1 = *reinterpret_cast<const float4*>(brow + 64 + tx * 4);
+        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float d[8][8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) d[r][q] = av[r] - bv[q];
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[r][q] += fabsf(d[r][q]);
+    }
+}
+
+template <int KC_, int STAGES_, int UNROLL, bool PACKED, bool PRODW>
+__global__ void __launch_bounds__(PRODW ? PAIR_THREADS + 32 : PAIR_THREADS, 2)
+pairwise_l1_v2_kernel(const __grid_constant__ CUtensorMap tmap, const PairArgs p) {
+    using Smem = PairSmemV2<KC_, STAGES_>;
+    constexpr uint32_t BYTES = 2u * KC_ * TILE * sizeof(float);
+    extern __shared__ __align__(128) unsigned char pair_smem_raw[];
+    Smem& sm = *reinterpret_cast<Smem*>(pair_smem_raw);
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES_; ++s) {
+            mbar_init(smem_u32(&sm.full[s]), 1);
+            mbar_init(smem_u32(&sm.empty[s]), PAIR_THREADS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int k_chunks = p.k_chunks;
+    auto tile_origin = [&](int t, int& I, int& J) {
+        if (p.symmetric) {
+            tri_decode(t * p.tile_stride + p.tile_offset, p.tiles_r, p.tiles_c, I, J);
+        } else {
+            I = t / p.tiles_c;
+            J = t - I * p.tiles_c;
+        }
+    };
+
+    // ---- producer cursor: walks (tile, chunk) of this CTA's tile list, one stage per chunk ----
+    int pt = blockIdx.x, pc = 0, ps = 0, pi_base = 0, pj_base = 0;
+    uint32_t pph = 0;
+    auto produce_one = [&]() {
+        if (pt >= p.n_tiles) return;
+        if (pc == 0) {
+            int I, J;
+            tile_origin(pt, I, J);
+            pi_base = p.row0 + I * TILE;
+            pj_base = p.col0 + J * TILE;
+        }
+        mbar_wait(smem_u32(&sm.empty[ps]), pph ^ 1u);
+        const uint32_t full = smem_u32(&sm.full[ps]);
+        mbar_expect_tx(full, BYTES);
+        tma_load_2d(smem_u32(&sm.a[ps][0][0]), &tmap, pi_base, pc * KC_, full);
+        tma_load_2d(smem_u32(&sm.b[ps][0][0]), &tmap, pj_base, pc * KC_, full);
+        if (++pc == k_chunks) { pc = 0; pt += gridDim.x; }
+        if (++ps == STAGES_) { ps = 0; pph ^= 1u; }
+    };
+
+    if (PRODW) {
+        if (tid >= PAIR_THREADS) {
+            if (tid == PAIR_THREADS)
+                while (pt < p.n_tiles) produce_one();
+            return;
+        }
+    } else if (tid == 0) {
+        for (int n = 0; n < p.lookahead; ++n) produce_one();
+    }
+
+    // ===== consumers: 16 x 16 threads, each 8 x 8 outputs (2 x 2 blocks of 4 x 4) =====
+    const int tx = tid & 15, ty = tid >> 4;
+    float acc[8][8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+
+    int s = 0;
+    uint32_t ph = 0, ready = 0;
+    const int row_end = p.row0 + p.n_rows, col_end = p.col0 + p.n_cols;
+    for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+        for (int c = 0; c < k_chunks; ++c) {
+            if (!PRODW && tid == 0) produce_one();
+            if (!ready) mbar_wait(smem_u32(&sm.full[s]), ph);
+            const int ns = (s + 1 == STAGES_) ? 0 : s + 1;
+            const uint32_t nph = (ns == 0) ? ph ^ 1u : ph;
+            // look at the NEXT chunk's barrier now (its TMA was issued long ago): the round trip
+            // hides under this chunk's FADDs instead of heading the next chunk's dependency chain
+            ready = mbar_probe(smem_u32(&sm.full[ns]), nph);
+            // One rolled loop of 8-k-step bodies serves full chunks and the (shorter) last chunk alike.
+            // The body must stay ~17 KB of SASS: when ptxas sees a constant trip count it peels the
+            // first iteration, the chunk becomes 34 KB of straight-line code (> 32 KB instruction
+            // cache) and the warps stall on instruction fetch (measured: 69 % instead of 84 %).
+            const int kn = (c + 1 < k_chunks) ? KC_ : p.k_last;   // valid rows of this chunk, multiple of 4
+            int kk = 0;
+#pragma unroll 1
+            for (; kk + UNROLL <= kn; kk += UNROLL) {
+#pragma unroll
+                for (int j = 0; j < UNROLL; ++j)
+                    pair_kstep<PACKED>(&sm.a[s][kk + j][0], &sm.b[s][kk + j][0], ty, tx, acc);
+            }
+#pragma unroll 1
+            for (; kk < kn; kk += 4) {      // remainder of the last chunk, groups of 4 rows
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    pair_kstep<PACKED>(&sm.a[s][kk + j][0], &sm.b[s][kk + j][0], ty, tx, acc);
+            }
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(smem_u32(&sm.empty[s]));
+            s = ns;
+            ph = nph;
+        }
+
+        // ---- epilogue: direct store (+ mirrored store for off-diagonal symmetric tiles) ----
+        int I, J;
+        tile_origin(t, I, J);
+        const int i_base = p.row0 + I * TILE, j_base = p.col0 + J * TILE;
+        const bool full_tile = (i_base + TILE <= row_end) && (j_base + TILE <= col_end) && p.vec_ok;
+        if (full_tile) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int i = i_base + (r < 4 ? ty * 4 + r : 64 + ty * 4 + (r - 4));
+                float* o = row_ptr(p, i) + j_base;
+                *reinterpret_cast<float4*>(o + tx * 4) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+                *reinterpret_cast<float4*>(o + 64 + tx * 4) = make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]);
+            }
+            if (p.symmetric && I != J) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int j = j_base + (q < 4 ? tx * 4 + q : 64 + tx * 4 + (q - 4));
+                    float* o = row_ptr(p, j) + i_base;
+                    *reinterpret_cast<float4*>(o + ty * 4) = make_float4(acc[0][q], acc[1][q], acc[2][q], acc[3][q]);
+                    *reinterpret_cast<float4*>(o + 64 + ty * 4) = make_float4(acc[4][q], acc[5][q], acc[6][q], acc[7][q]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int i = i_base + (r < 4 ? ty * 4 + r : 64 + ty * 4 + (r - 4));
+                if (i >= row_end) continue;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int j = j_base + (q < 4 ? tx * 4 + q : 64 + tx * 4 + (q - 4));
+                    if (j >= col_end) continue;
+                    row_ptr(p, i)[j] = acc[r][q];
+                    if (p.symmetric && I != J) row_ptr(p, j)[i] = acc[r][q];
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+    }
+}
+
 // ---- FP32 issue-peak probe: same instruction mix as the inner loop, no memory ----
 __global__ void __launch_bounds__(256, 2) fp32_peak_probe_kernel(float* sink, int iters) {
     float a[8], b[8], acc[8][8];
@@ -444,8 +673,100 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 
 namespace hsd {
 
+// ---- v2 dispatch ----
+struct V2Config { int kc, stages, packed, prodw, lookahead, unroll; };
+
+static V2Config v2_config() {
+    // HSD_PAIR_V2="kc,stages,packed,prodw,lookahead,unroll" (tuning knob, read once); "0" = round-1 kernels
+    static V2Config cfg = {-1, 0, 0, 0, 0, 0};
+    if (cfg.kc < 0) {
+        V2Config c = {HSD_PAIR_V2_DEFAULT};
+        const char* e = getenv("HSD_PAIR_V2");
+        if (e) {
+            int v[6] = {c.kc, c.stages, c.packed, c.prodw, c.lookahead, c.unroll};
+            int n = 0;
+            const char* q = e;
+            while (n < 6 && *q) {
+                v[n++] = atoi(q);
+                while (*q && *q != ',') ++q;
+                if (*q == ',') ++q;
+            }
+            c = {v[0], v[1], v[2], v[3], v[4], v[5]};
+        }
+        cfg = c;
+    }
+    return cfg;
+}
+
+template <int KC_, int STAGES_, bool PACKED, bool PRODW, int UNROLL = 8>
+static int launch_v2(const CUtensorMap& tmap, const PairArgs& a, cudaStream_t stream, int sms) {
+    auto kern = pairwise_l1_v2_kernel<KC_, STAGES_, UNROLL, PACKED, PRODW>;
+    const int smem = (int)sizeof(PairSmemV2<KC_, STAGES_>);
+    HSD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int grid = (int)std::min<long long>(a.n_tiles, 2ll * sms);
+    kern<<<grid, PRODW ? PAIR_THREADS + 32 : PAIR_THREADS, smem, stream>>>(tmap, a);
+    HSD_CUDA_TRY(cudaGetLastError());
+    return HSD_OK;
+}
+
+static int encode_table(CUtensorMap* tmap, const float* sigT, int32_t k_rows, int64_t n_pad, int box_n, int box_k) {
+    auto encode = get_encode();
+    if (!encode) {
+        set_error("cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+        return HSD_ERR_NO_DEVICE;
+    }
+    // rows >= k_rows and columns >= n_pad are out of bounds: TMA fills them with zeros
+    const cuuint64_t gdim[2] = {(cuuint64_t)n_pad, (cuuint64_t)k_rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)n_pad * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)box_n, (cuuint32_t)box_k};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult cr = encode(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(sigT), gdim,
+                         gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
+        return HSD_ERR_CUDA;
+    }
+    return HSD_OK;
+}
+
+static int launch_pairwise_v2(const V2Config& c, const float* sigT, int32_t k_used, int64_t n_pad, PairArgs a,
+                              long long n_tiles, cudaStream_t stream) {
+    HSD_REQUIRE(n_tiles < (1ll << 31), "too many tiles for one launch");
+    if (n_tiles <= 0) return HSD_OK;
+    CUtensorMap tmap;
+    const int rc = encode_table(&tmap, sigT, k_used, n_pad, TILE, c.kc);
+    if (rc != HSD_OK) return rc;
+    a.k_chunks = (k_used + c.kc - 1) / c.kc;
+    a.k_last = ((k_used - (a.k_chunks - 1) * c.kc) + 3) / 4 * 4;
+    a.n_tiles = (int)n_tiles;
+    a.lookahead = std::max(1, std::min(c.lookahead, c.stages - 1));
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+#define HSD_V2_CASE(KC_, ST_)                                                                        \
+    if (c.kc == KC_ && c.stages == ST_) {                                                            \
+        if (c.packed && !c.prodw && c.unroll == 16)                                                  \
+            return launch_v2<KC_, ST_, true, false, 16>(tmap, a, stream, sms);                       \
+        if (c.packed && c.prodw) return launch_v2<KC_, ST_, true, true>(tmap, a, stream, sms);       \
+        if (c.packed) return launch_v2<KC_, ST_, true, false>(tmap, a, stream, sms);                 \
+        if (c.prodw) return launch_v2<KC_, ST_, false, true>(tmap, a, stream, sms);                  \
+        return launch_v2<KC_, ST_, false, false>(tmap, a, stream, sms);                              \
+    }
+    HSD_V2_CASE(16, 4)
+    HSD_V2_CASE(16, 6)
+    HSD_V2_CASE(32, 3)
+#undef HSD_V2_CASE
+    set_error("HSD_PAIR_V2: unsupported kc/stages %d/%d (16/4, 16/6, 32/3)", c.kc, c.stages);
+    return HSD_ERR_INVALID;
+}
+
 static int launch_pairwise(const float* sigT, int32_t k_used, int64_t n_pad, PairArgs a, long long n_tiles,
                            cudaStream_t stream) {
+    {
+        const V2Config c = v2_config();
+        if (c.kc > 0) return launch_pairwise_v2(c, sigT, k_used, n_pad, a, n_tiles, stream);
+    }
     const int32_t k_pad = (k_used + KC - 1) / KC * KC;
     auto encode = get_encode();
     if (!encode) {

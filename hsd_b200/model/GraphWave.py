@@ -12,6 +12,7 @@ import torch
 from .. import engine, wavelets as _wav
 from ..graph import CSRGraph
 from ..tools import util
+from ._device import on_model_device
 
 
 class GraphWave(object):
@@ -24,7 +25,7 @@ class GraphWave(object):
         self.nodes = list(nx.nodes(graph))
         self.idx2node, self.node2idx = util.build_node_idx_map(graph)
         self.csr = CSRGraph.from_networkx(graph)
-        self.device = device or engine.require_cuda()
+        self.device = torch.device(device) if device is not None else engine.require_cuda()
         self.adjacent = nx.adjacency_matrix(graph).todense()
         self.laplacian = nx.laplacian_matrix(graph).todense()
         L = torch.as_tensor(np.asarray(self.laplacian, dtype=np.float64), device=self.device)
@@ -34,10 +35,14 @@ class GraphWave(object):
         self.wavelets = None
         self.lmax = None
 
+    def _device(self):
+        return self.device
+
+    @on_model_device
     def calculate_wavelets(self, scale, approx=True) -> np.ndarray:
         if approx:
             if self.lmax is None:
-                self.lmax = _wav.estimate_lmax(self.csr)
+                self.lmax = _wav.estimate_lmax(self.csr, device=self.device)
             psi = _wav.cheb_wavelets_dense(_wav.DeviceCSR(self.csr, self.device), float(scale), self.lmax,
                                            self.CHEB_ORDER, self.THRESHOLD_COEFF)
         else:
@@ -47,6 +52,7 @@ class GraphWave(object):
         self.wavelets = psi.cpu().numpy()
         return self.wavelets
 
+    @on_model_device
     def calculate_characteristic_value(self, X: np.ndarray, sample_points):
         """model/GraphWave.py:53-59: [Re, Im] of mean(exp(i t X)) per sample point."""
         x = torch.as_tensor(np.asarray(X, dtype=np.float64), device=self.device).reshape(1, -1)
@@ -64,6 +70,7 @@ class GraphWave(object):
                                                   engine._stream()))
         return out
 
+    @on_model_device
     def embed(self, sample_points):
         assert self.wavelets is not None, "GraphWave wavelets is None!"
         psi = torch.as_tensor(np.asarray(self.wavelets, dtype=np.float64), device=self.device)

@@ -25,6 +25,7 @@ from .. import engine, rings as _rings, wavelets as _wav
 from ..graph import CSRGraph, has_nonunit_weights
 from ..tools import hierarchy as _hierarchy
 from ..tools import util
+from ._device import on_model_device
 
 
 class HSD(object):
@@ -96,7 +97,8 @@ class HSD(object):
     @property
     def hierarchy(self):
         if self._hierarchy is None and self._hierarchy_lazy:
-            self._hierarchy = self._rings().to_hierarchy(self.nodes)
+            with torch.cuda.device(self._device()):
+                self._hierarchy = self._rings().to_hierarchy(self.nodes)
             self._ringset_src = self._hierarchy   # same rings: keep the device copy
             self._hierarchy_lazy = False
         return self._hierarchy
@@ -108,7 +110,12 @@ class HSD(object):
 
     # ---- device state ----
     def _device(self):
-        return self.device or engine.require_cuda()
+        """The CUDA device of this model (the ctor's `device`, else the current device).  The C
+        library launches on the CURRENT device, so every public entry point that reaches a
+        kernel runs under `torch.cuda.device(self._device())` (see _on_model_device)."""
+        if self.device is None:
+            return engine.require_cuda()
+        return torch.device(self.device)
 
     def _device_graph(self, include_zero=False) -> engine.DeviceGraph:
         if self._dg is None or self._dg.include_zero != include_zero:
@@ -159,7 +166,7 @@ class HSD(object):
                 raise NotImplementedError("the Chebyshev kernel takes unit edge weights; use approx=False "
                                           "(dense eigh honours weights like the reference)")
             if self.lmax is None:
-                self.lmax = _wav.estimate_lmax(self.csr)
+                self.lmax = _wav.estimate_lmax(self.csr, device=self._device())
             return _wav.cheb_wavelets_dense(self._device_csr(), float(scale), self.lmax,
                                             self.CHEB_ORDER, self.THRESHOLD_COEFF)
         if self.eigenvalues is not None and self.eigenvectors is not None:
@@ -170,18 +177,21 @@ class HSD(object):
         L = torch.as_tensor(np.asarray(self.L, dtype=np.float64), device=self._device())
         return _wav.exact_wavelets_dense(L, float(scale), self.THRESHOLD_COEFF, eig)
 
+    @on_model_device
     def calculate_wavelets(self, scale, approx=True) -> np.ndarray:
         psi = self._wavelets_device(scale, approx)
         self.wavelets = psi.cpu().numpy()
         return self.wavelets
 
     # model/HSD.py:71-83
+    @on_model_device
     def get_hierarchical_coeffcients(self, wavelets) -> dict:
         mem = self._rings().members_host()
         w = np.asarray(wavelets)
         return {node: [list(w[i, layer]) for layer in mem[i]] for i, node in enumerate(self.nodes)}
 
     # model/HSD.py:87-94
+    @on_model_device
     def get_nodes_hierarchical_degree(self) -> dict:
         sizes = self._rings().sizes.cpu().numpy()
         out = {}
@@ -193,6 +203,7 @@ class HSD(object):
         return out
 
     # ---- distances ----
+    @on_model_device
     def structural_distance_device(self, scale=None, approx=False) -> torch.Tensor:
         """Device-resident result (float32 in degree mode, float64 in wavelet mode)."""
         if self.signal == "degree":
@@ -202,6 +213,7 @@ class HSD(object):
         psi = self._wavelets_device(self.scale if scale is None else scale, approx)
         return _rings.value_distance(psi, self._rings(), 0, self.hop + 1, mode="w1")
 
+    @on_model_device
     def calculate_structural_distance(self, scale, approx=False, out=None):
         """model/HSD.py:98-114: D[i, j] = sum_{h=0..hop} W1(ring signal_i[h], ring signal_j[h]).
         Returns a float64 ndarray like the reference; ``out`` (a pinned float32/float64
@@ -210,9 +222,20 @@ class HSD(object):
             # host-buffer pipeline: H2D of the CSR, kernels, and the D2H of finished row panels
             # overlapped with the panels still computing (engine.HostDegreePipeline)
             dst = out if isinstance(out, torch.Tensor) else torch.from_numpy(out)
-            if self._host_pipe is None or self._host_pipe.g is not self.csr or self._host_pipe.hops != self.hop:
-                self._host_pipe = engine.HostDegreePipeline(self.csr, self.hop, empty=self.empty, device=self._device())
-            self._host_pipe.run(dst)
+            pipe = self._host_pipe
+            if pipe is None or pipe.g is not self.csr or pipe.hops != self.hop or pipe.empty != self.empty:
+                pipe = self._host_pipe = engine.HostDegreePipeline(self.csr, self.hop, empty=self.empty,
+                                                                   device=self._device())
+            if dst.dtype == torch.float32:
+                pipe.run(dst)
+            elif dst.dtype == torch.float64:
+                # the kernels produce float32: stage through a pinned float32 buffer, widen on the host
+                if getattr(self, "_host_stage", None) is None or self._host_stage.shape != dst.shape:
+                    self._host_stage = torch.empty(dst.shape, dtype=torch.float32).pin_memory()
+                pipe.run(self._host_stage)
+                dst.copy_(self._host_stage)
+            else:
+                raise ValueError("out must be float32 or float64")
             return out
         D = self.structural_distance_device(scale, approx)
         if out is not None:
@@ -221,6 +244,7 @@ class HSD(object):
             return out
         return D.cpu().numpy().astype(np.float64, copy=False)
 
+    @on_model_device
     def nearest_neighbors(self, k, scale=None, approx=False):
         """(idx, dist): the k structurally closest nodes of every node, selected on the device
         from the resident distance matrix — what a precomputed-metric KNN (tools/evaluate.py:61-69)
@@ -231,6 +255,7 @@ class HSD(object):
         idx, val = engine.topk_rows(D.contiguous(), k)
         return idx.cpu().numpy(), val.cpu().numpy()
 
+    @on_model_device
     def parallel_calculate_HSD(self, n_workers=3, row_signal="reference"):
         """model/HSD.py:118-137 with the worker of :140-161: hops 0..hop-1 of the zero-padded
         'aligned' distance (tools/metrics.py:151-192).  row_signal="reference" reproduces the

@@ -28,6 +28,7 @@ from .. import engine
 from ..graph import CSRGraph
 from ..tools import util
 from .multiscale_HSD import MultiHSD
+from ._device import on_model_device
 
 
 class DynamicHSD(MultiHSD):
@@ -94,6 +95,7 @@ class DynamicHSD(MultiHSD):
             self._refresh_graph()
 
     # ---- incremental distance (degree signal) ----
+    @on_model_device
     def affected_nodes_device(self) -> torch.Tensor:
         """Original indices of nodes within ``hop`` hops of a pending endpoint (int64, sorted)."""
         dg = self._device_graph(include_zero=(self.empty == "zero"))
@@ -113,12 +115,17 @@ class DynamicHSD(MultiHSD):
         bits = _unpack_bits(ball, dg.n)
         return torch.sort(dg.orig_of[bits].to(torch.int64)).values
 
+    @on_model_device
     def structural_distance_update(self) -> torch.Tensor:
         """Distance matrix of the current graph (device, float32).  After insertions only the
         affected rows / columns are recomputed; equals a from-scratch recompute bit for bit
         because every entry is produced by the same kernel from the same signatures."""
         if self.signal != "degree":
-            self._D = self.structural_distance_device(self.scale, approx=True)
+            # wavelet signal: MultiHSD's distance is the sum over self.scales
+            # (model/multiscale_HSD.py:101-119); self.scale is 0 for a MultiHSD (exp(-0 L) = I would
+            # give an all-zero matrix).  Every Psi_s changes globally with the graph: full recompute.
+            self.init_scales()
+            self._D = self.structural_distance_multiscale_device()
             self._pending.clear()
             return self._D
         dg = self._device_graph(include_zero=(self.empty == "zero"))
@@ -157,6 +164,7 @@ class DynamicHSD(MultiHSD):
         self._pending.clear()
         return self._D
 
+    @on_model_device
     def structural_distance_update_sharded(self, rank: int, world: int, group=None, peer: bool = True) -> torch.Tensor:
         """structural_distance_update() on `world` GPUs (one process per GPU, every process applies
         the same insertions): returns this rank's row block [shard_rows(n, world, rank)] of the
@@ -181,6 +189,7 @@ class DynamicHSD(MultiHSD):
         return blk
 
     # ---- exploratory helpers of the reference ----
+    @on_model_device
     def explore_neighborhoods(self, node, maxHop=5) -> set:
         """model/dynamic_HSD.py:28-43: BFS layers of one node, stored in ``self.hierarchy[node]``;
         returns every node within ``self.hop`` hops.  (The reference discards the result of

@@ -17,6 +17,7 @@ import torch
 from .. import engine, wavelets as _wav
 from .._lib import check, lib
 from .HSD import HSD
+from ._device import on_model_device
 
 
 def _ring_reduce(psiT, n_scales, n, n_cols, rings, sizes, hops, col0, emb):
@@ -38,6 +39,7 @@ class MultiHSD(HSD):
         self.embeddings = None
         self.init()
 
+    @on_model_device
     def init(self):
         """model/multiscale_HSD.py:26-31: scales from the (estimated) largest Laplacian
         eigenvalue; rings from a .layers file when one is configured, else the BFS kernel."""
@@ -45,11 +47,12 @@ class MultiHSD(HSD):
             self.scales = np.zeros(1)   # the degree signal has no scale axis
         else:
             if self.lmax is None:
-                self.lmax = _wav.estimate_lmax(self.csr)
+                self.lmax = _wav.estimate_lmax(self.csr, device=self._device())
             self.scales = np.exp(np.linspace(np.log(0.01), np.log(self.lmax * 1.25), self.n_scales))
         super(MultiHSD, self).init()
 
     # ---- batched device path ----
+    @on_model_device
     def embed_device(self, approx=True, stat="triple", col_range=None) -> torch.Tensor:
         """emb[N, n_scales, hop+1, 2] float64 = [sum, mean] of Psi_s[i, ring_h(i)].
         col_range=(begin, end) restricts the work to those nodes' impulse columns (rows of emb
@@ -67,7 +70,7 @@ class MultiHSD(HSD):
                 raise NotImplementedError("the Chebyshev kernel takes unit edge weights; use approx=False")
             csr = self._device_csr()
             if self.lmax is None:
-                self.lmax = _wav.estimate_lmax(self.csr)
+                self.lmax = _wav.estimate_lmax(self.csr, device=self._device())
             for s0 in range(0, len(scales), 8):
                 sc = scales[s0:s0 + 8]
                 coeffs = np.stack([_wav.cheby_coefficients(s, self.lmax, self.CHEB_ORDER) for s in sc])
@@ -95,6 +98,7 @@ class MultiHSD(HSD):
                 emb[:, si:si + 1] = part
         return emb
 
+    @on_model_device
     def embed_device_sharded(self, rank: int, world: int, group=None) -> torch.Tensor:
         """Multi-GPU embed (SURVEY.md §8 e): every rank owns whole Chebyshev recurrences for a
         contiguous block of impulse columns (graph and rings replicated), computes the ring
@@ -136,10 +140,12 @@ class MultiHSD(HSD):
         _ring_reduce(row.view(1, self.n_node, 1), 1, self.n_node, 1, rings, rings.sizes.contiguous(), self.hop, i, part)
         return part[i, 0].cpu().numpy()
 
+    @on_model_device
     def get_triple(self, wavelets: np.ndarray, node: str) -> list:
         """model/multiscale_HSD.py:45-61: [sum, mean] per hop, [0, 0] for an empty ring."""
         return self._ring_stats_of_row(wavelets, node).reshape(-1).tolist()
 
+    @on_model_device
     def get_layer_sum(self, wavelets: np.ndarray, node: str) -> list:
         """model/multiscale_HSD.py:64-73: ring sums only."""
         return self._ring_stats_of_row(wavelets, node)[:, 0].tolist()
@@ -149,11 +155,24 @@ class MultiHSD(HSD):
         self.embeddings = self.embed()
         return self.embeddings
 
+    @on_model_device
+    def init_scales(self):
+        """(Re)compute lmax and the scale grid (model/multiscale_HSD.py:27-30) if the graph changed."""
+        if self.signal != "degree" and self.lmax is None:
+            self.lmax = _wav.estimate_lmax(self.csr, device=self._device())
+            self.scales = np.exp(np.linspace(np.log(0.01), np.log(self.lmax * 1.25), self.n_scales))
+
+    @on_model_device
+    def structural_distance_multiscale_device(self) -> torch.Tensor:
+        """Device-resident float64 sum over self.scales of the Chebyshev-wavelet HSD matrix."""
+        total = None
+        for scale in self.scales:
+            D = HSD.structural_distance_device(self, float(scale), approx=True)
+            total = D.to(torch.float64) if total is None else total + D
+        return total
+
     def parallel_calculate_structural_distance(self, n_workers: int = None):
         """model/multiscale_HSD.py:101-119: sum over scales of
         HSD.calculate_structural_distance(scale, approx=True)."""
-        total = None
-        for scale in self.scales:
-            D = self.structural_distance_device(float(scale), approx=True)
-            total = D.to(torch.float64) if total is None else total + D
-        return total.cpu().numpy()
+        with torch.cuda.device(self._device()):
+            return self.structural_distance_multiscale_device().cpu().numpy()

@@ -56,6 +56,18 @@ def deal_affected(aff: torch.Tensor, n: int, world: int, rank: int):
     return dealt, segments
 
 
+def agree_status(status: torch.Tensor, world: int, group=None) -> int:
+    """OR of every rank's status flags (a MAX all-reduce of the bit field would lose bits, so the
+    flags are summed per bit).  world == 1, or no process group: the local value."""
+    if world > 1:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            bits = torch.stack([(status.reshape(-1)[0] >> b) & 1 for b in range(8)]).to(torch.int32)
+            dist.all_reduce(bits, op=dist.ReduceOp.SUM, group=group)
+            return int(sum((1 << b) for b, v in enumerate(bits.tolist()) if v))
+    return int(status.reshape(-1)[0].item())
+
+
 class ShardedDegreeHSD:
     """Plan + buffers for repeated evaluation of one graph on `world` ranks."""
 
@@ -384,5 +396,12 @@ class ShardedDegreeHSD:
         return self.distances()
 
     def check(self) -> None:
-        if self.empty == "raise" and int(self.status.item()) & 1:
+        """Raise where scipy would (an empty ring under empty='raise') — on EVERY rank: the BFS
+        kernel flags only the sources dealt to this rank, so the flags are OR-ed over the ranks
+        first; otherwise the ranks that own no such source would carry on with a block built from
+        all-zero signature rows and hang at the next barrier once the raising rank is gone."""
+        if self.empty != "raise":
+            return
+        flags = agree_status(self.status, self.world if not hasattr(self, "blocks") else 1, self.group)
+        if flags & 1:
             raise engine.EmptyRingError("Distribution can't be empty.")

@@ -4,7 +4,8 @@ sys.path.insert(0, ".")
 import numpy as np, torch, networkx as nx
 from hsd_b200 import engine, rings
 from hsd_b200.graph import powerlaw_graph
-from model import HSD, MultiHSD, GraphWave
+from model import HSD, MultiHSD
+from model.GraphWave import GraphWave
 
 g = powerlaw_graph(301, 3, seed=0)
 dg = engine.DeviceGraph.upload(g)

@@ -89,3 +89,29 @@ def test_world2_incremental_update_deals_every_affected_row_to_its_owner(n, aff)
     assert all(ret[r][0] and ret[r][1] for r in range(world))
     assert sum(ret[r][2] for r in range(world)) == len(aff)
     assert abs(ret[0][2] - ret[1][2]) <= 1                 # balanced whatever block the rows fall into
+
+
+def _status_worker(rank, world, port, flags, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from hsd_b200.sharded import agree_status
+    status = torch.tensor([flags[rank]], dtype=torch.int32)      # what the BFS kernel left on this rank
+    ret[rank] = agree_status(status, world)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("flags,want", [((1, 0), 1), ((0, 0), 0), ((0, 1), 1), ((2, 1), 3)])
+def test_world2_empty_ring_flag_is_global(flags, want):
+    """an isolated node is BFS-ed by ONE rank; every rank must see its empty-ring flag so
+    that all of them raise (or none), instead of one raising and the others hanging at a barrier."""
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    procs = [ctx.Process(target=_status_worker, args=(r, world, port, flags, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert ret[0] == want and ret[1] == want

@@ -216,9 +216,11 @@ def test_degree_signal_model_and_multiscale_sum(golden_graphs, golden_runs):
 def test_graphwave_barbell_classes(golden_graphs):
     """The only assertion in the reference's tests (tests/graphwave_test/main.py:47-50):
     nodes of one structural class have embeddings within L1 < 1e-3."""
-    from model import GraphWave
+    from model import GraphWave      # the MODULE, as tests/graphwave_test/main.py:12,33-34 uses it
     g = nx_graph(golden_graphs, "barbell")
-    gw = GraphWave(g)
+    gw = GraphWave.GraphWave(g)
+    lo, hi = GraphWave.recommend_scale_range(gw.eigenvalues)
+    assert 0 < lo < hi
     gw.calculate_wavelets(2.5, approx=False)
     emb = gw.embed(np.linspace(0, 50, 100))
     labels = golden_graphs["barbell_labels"]

@@ -251,3 +251,49 @@ def test_weighted_edge_detection_and_identity_label_fast_path():
     e = np.array(base.edges(), dtype=np.int64)
     c = CSRGraph.from_edges(200, e)
     assert np.array_equal(a.rowptr, c.rowptr) and np.array_equal(a.col, c.col)
+
+
+def test_drop_in_import_paths():
+    """Every import form the reference's own callers use resolves: the package
+    re-exports the three classes (model/__init__.py:2-4), the submodules are importable by
+    path (tests/robust_test/main.py:11) and `model.GraphWave` is the module
+    (tests/graphwave_test/main.py:12,33-34)."""
+    import sys
+    import types
+    from model import HSD, MultiHSD, DynamicHSD
+    from model.HSD import HSD as H2
+    from model.multiscale_HSD import MultiHSD as M2
+    from model.dynamic_HSD import DynamicHSD as D2
+    from model import GraphWave
+    assert HSD is H2 and MultiHSD is M2 and DynamicHSD is D2
+    assert isinstance(GraphWave, types.ModuleType) and isinstance(sys.modules["model.HSD"], types.ModuleType)
+    assert isinstance(GraphWave.GraphWave, type) and callable(GraphWave.recommend_scale_range)
+    from tools import hierarchy, util, save_vectors_dict   # model/multiscale_HSD.py:12, tools/multiscales.py:11
+    from tools.hierarchy import get_hierarchical_representation, read_hierarchy
+    assert callable(get_hierarchical_representation) and callable(read_hierarchy) and callable(save_vectors_dict)
+
+
+def test_calculate_distance_metric_names_and_exceptions():
+    """tools/metrics.py:151-192: same exception types as the reference for every metric name."""
+    from tools.metrics import calculate_distance
+    p, q = [0.2, 0.3, 0.5], [0.5, 0.25, 0.25]
+    # values printed by the unmodified reference (tools/metrics.py imported by path) on the same input
+    assert abs(calculate_distance(p, q, "l1") - 0.09999999999999998) < 1e-15
+    assert abs(calculate_distance(p, q, "kl") - 0.010067756775344432) < 1e-15
+    assert abs(calculate_distance(p, q, "symmetric_kl") - 0.010136627702704112) < 1e-15
+    assert abs(calculate_distance(p, q, "wasserstein_guass") - 4.7207654837878865e-05) < 1e-18
+    assert abs(calculate_distance(p, q, "l2") - (0.05 ** 2 + 0.05 ** 2)) < 1e-12
+    ps, qs = np.sort(p), np.sort(q)
+    assert abs(calculate_distance(p, q, "kl") - float(np.sum(ps * np.log(ps / qs)))) < 1e-12
+    sym = (np.sum(ps * np.log(ps / qs)) + np.sum(qs * np.log(qs / ps))) / 2
+    assert abs(calculate_distance(p, q, "symmetric_kl") - sym) < 1e-12
+    for m in ("l1", "l2", "kl", "symmetric_kl", "js"):
+        with pytest.raises(ValueError):                                  # un-normalised ring signals
+            calculate_distance([1.0, 2.0], [3.0], m)
+    with pytest.raises(ValueError):                                      # m = p + q sums to 2 (as written, :103-105)
+        calculate_distance(p, q, "js")
+    with pytest.raises(NotImplementedError):
+        calculate_distance(p, q, "dtw")
+    with pytest.raises(TypeError):
+        calculate_distance(p, q, None)
+    assert calculate_distance([], [], "l1") == 0.0

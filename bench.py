@@ -51,7 +51,22 @@ def parse_workload(spec: str):
 _POOL_STATE = {}
 
 
+def _cap_threads():
+    """One thread per worker process: scipy's W1 ends in a BLAS dot, and a forked worker otherwise
+    inherits a BLAS/OpenMP pool as wide as the machine — `cores` processes x `cores` spinning threads
+    made the round-1 reference arm 85x slower without torchrun (which exports OMP_NUM_THREADS=1)
+    than with it.  Environment for pools created later, threadpoolctl for the ones already loaded."""
+    for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+        os.environ[k] = "1"
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
+
+
 def _pool_init(n, edges, hops):
+    _cap_threads()
     from oracle import hsd_oracle as O
     _POOL_STATE["adj"] = O.adjacency_from_edges(n, edges)
     _POOL_STATE["hops"] = hops
@@ -84,7 +99,8 @@ class CpuReference:
         self.n, self.hops = n, hops
         g = nx.barabasi_albert_graph(n, 5, seed=seed)
         self.edges = np.array(g.edges(), dtype=np.int64)
-        self.cores = os.cpu_count() or 1
+        self.cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        _cap_threads()      # before the fork: the workers inherit single-threaded BLAS/OpenMP pools
         self.sample = np.sort(np.random.default_rng(seed).choice(n, size=min(sample_nodes, n), replace=False))
         self.pool = mp.get_context("fork").Pool(self.cores, initializer=_pool_init,
                                                 initargs=(n, self.edges, hops))
@@ -114,8 +130,8 @@ class CpuReference:
     def describe(self, d):
         return (f"{d['sample_nodes']} sampled sources: Python BFS rings ({d['ring_cpu_s_per_source']*1e3:.1f} ms/source) + "
                 f"{d['sample_pairs']} pairs x {self.hops + 1} hops of scipy wasserstein_distance "
-                f"({d['pair_cpu_s']*1e6:.0f} us/pair), extrapolated to N={self.n} on {self.cores} cores "
-                f"(perfect scaling assumed)")
+                f"({d['pair_cpu_s']*1e6:.0f} us/pair), extrapolated to N={self.n} on {self.cores} worker processes, "
+                f"one thread each (OMP/MKL/OPENBLAS_NUM_THREADS=1 + threadpoolctl; perfect scaling assumed)")
 
     def close(self):
         self.pool.close()

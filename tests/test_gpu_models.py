@@ -285,3 +285,45 @@ def test_reference_main_py_flow(golden_graphs):
     assert m2.embeddings is emb
     nodes0 = m2.hierarchy[m2.nodes[0]]
     assert nodes0[0] == [m2.nodes[0]] and len(nodes0) == 4
+
+
+@pytest.mark.parametrize("name,hop,n_scales,n_pairs", [("karate", 3, 3, None), ("europe", 3, 3, 400)])
+def test_multiscale_distance_matches_oracle_sum_over_scales(golden_graphs, name, hop, n_scales, n_pairs):
+    """a15 — MultiHSD.parallel_calculate_structural_distance (model/multiscale_HSD.py:101-119) against
+    the oracle's  sum_s structural_distance_from_coeffs(hierarchical_coefficients(cheby_wavelets(s)))
+    (model/HSD.py:50-66, 71-83, 98-114), scipy W1 per pair and hop; lmax and scales shared with the
+    oracle (pygsp's ARPACK estimate is not reproducible).  karate: every pair; europe: 400
+    sampled pairs (each oracle pair costs 4 hops x 3 scales scipy calls).  Also checks the
+    DynamicHSD default (signal='wavelet') update returns this same, non-trivial matrix."""
+    from model import DynamicHSD, MultiHSD
+    g = nx_graph(golden_graphs, name)
+    mm = MultiHSD(g, name, hop, n_scales)
+    n = mm.n_node
+    adj = [np.array(sorted(mm.node2idx[w] for w in g.neighbors(v))) for v in mm.nodes]
+    L = O.laplacian_dense(adj)
+    lmax = O.estimate_lmax(L)
+    assert abs(mm.lmax - lmax) < 1e-3 * lmax             # the device power iteration finds the same eigenvalue
+    mm.lmax = lmax
+    mm.scales = O.multiscale_scales(lmax, n_scales)
+    rings = O.all_rings(adj, hop)
+    if n_pairs is None:
+        pairs = [(i, j) for i in range(n) for j in range(i + 1, n)]
+    else:
+        rng = np.random.default_rng(0)
+        pairs = sorted({tuple(sorted(p)) for p in rng.integers(0, n, size=(n_pairs, 2)).tolist() if p[0] != p[1]})
+    ref = np.zeros((n, n))
+    for s in mm.scales:
+        psi = O.cheby_wavelets(L, float(s), lmax, order=50, thr_coeff=1e-4)
+        ref += O.structural_distance_from_coeffs(O.hierarchical_coefficients(psi, rings), n, hop, pairs=pairs)
+    got = mm.parallel_calculate_structural_distance(4)
+    ii, jj = np.array(pairs).T
+    assert np.array_equal(got, got.T) and np.all(np.diag(got) == 0)
+    assert ref[ii, jj].max() > 1e-3                                      # a non-trivial matrix
+    # threshold flips (SURVEY H6) move one ring value by <= 1e-4/N: absolute floor per hop and scale
+    np.testing.assert_allclose(got[ii, jj], ref[ii, jj], rtol=1e-5, atol=(hop + 1) * n_scales * 1e-4 / n * 1e-3)
+    if name == "karate":
+        dyn = DynamicHSD(g, name, hop, n_scales)
+        dyn.lmax, dyn.scales = lmax, mm.scales
+        D = dyn.structural_distance_update().cpu().numpy()
+        np.testing.assert_allclose(D, got, rtol=1e-12, atol=1e-15)
+        assert D.max() > 1e-3

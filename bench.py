@@ -34,6 +34,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "HSD node-pairs/sec (3-hop distance matrix)"
 UNIT = "node-pairs/s"
+CPU_SAMPLE_NODES = 160   # 12 720 sampled pairs x (hops + 1) scipy calls ~ 10-30 s of CPU work per step
 
 
 def parse_workload(spec: str):
@@ -99,6 +100,7 @@ class CpuReference:
         self.n, self.hops = n, hops
         g = nx.barabasi_albert_graph(n, 5, seed=seed)
         self.edges = np.array(g.edges(), dtype=np.int64)
+        self.n_bins = int(np.unique(np.bincount(self.edges.ravel(), minlength=n)).size)   # distinct degrees
         self.cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
         _cap_threads()      # before the fork: the workers inherit single-threaded BLAS/OpenMP pools
         self.sample = np.sort(np.random.default_rng(seed).choice(n, size=min(sample_nodes, n), replace=False))
@@ -143,7 +145,7 @@ def run_reference(args):
     if rank != 0:
         return
     n, hops = parse_workload(args.workload)
-    ref = CpuReference(n, hops)
+    ref = CpuReference(n, hops, sample_nodes=CPU_SAMPLE_NODES)
     for _ in range(args.warmup):
         ref.step()
     vals, last = [], None
@@ -159,8 +161,7 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / max(args.steps, 1) * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"barabasi_albert_graph({n}, 5, seed=0), {hops} hops, degree-valued ring signal, full NxN",
-                   "n_nodes": n, "hops": hops},
+        "config": workload_config(n, hops, max(args.gpus, 1), args.gpus > 1 and not args.no_peer, ref.n_bins),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": ref.cores, "kind": "port",
                          "sample": ref.describe(last)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -248,39 +249,59 @@ def bind_to_gpu_numa_node(index):
 # ------------------------------------------------------------------------------
 # native arm
 # ------------------------------------------------------------------------------
-def run_native(args):
-    import torch
-    import torch.distributed as dist
-    from hsd_b200 import engine
-    from hsd_b200.graph import powerlaw_graph
-    from hsd_b200.sharded import ShardedDegreeHSD, shard_rows
+class Ctx:
+    """Per-process state of the native arm: rank / device / collectives helpers / peaks."""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py (native arm) needs a CUDA device: hsd_b200 has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    numa = bind_to_gpu_numa_node(local_rank)   # pinned host buffers then land on the GPU's own socket
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.args = torch, dist, args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py (native arm) needs a CUDA device: hsd_b200 has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        self.numa = bind_to_gpu_numa_node(self.local_rank)   # pinned host buffers land on the GPU's own socket
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.peer = self.world > 1 and not args.no_peer
+        self.flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=self.dev)  # > 126 MB L2
+        from hsd_b200 import engine
+        self.fp32_peak = engine.fp32_issue_peak()    # live FP32 CUDA-core issue peak (pairwise roofline denominator)
+        self.peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                self.peaks = json.load(f)
+        except Exception:
+            pass
+        self.hbm_peak = float(self.peaks.get("hbm_gbs", 6650.0))
+        self.hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if self.peaks else "fallback 6650 GB/s (of fallback)"
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
 
-    def max_over_ranks(x: float) -> float:
-        if world == 1:
+    def max_over_ranks(self, x: float) -> float:
+        if self.world == 1:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    n, hops = parse_workload(args.workload)
-    g = powerlaw_graph(n, 5, seed=0)       # same deterministic graph on every rank
+
+def measure_degree_path(ctx, g, hops, steps, warmup, workload_key):
+    """The hot path (rings -> signatures -> [fused all-gather] -> pairwise) on graph `g`, sharded over
+    ctx.world ranks: warm-up, then `steps` timed steps (CUDA events, barrier + synchronize on both
+    sides, max over ranks, L2 flushed before every step).  Returns (record, plan, dg)."""
+    torch = ctx.torch
+    from hsd_b200 import engine
+    from hsd_b200.sharded import ShardedDegreeHSD
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
+    n = g.n
     dg = engine.DeviceGraph.upload(g, device=dev)
-    peer = world > 1 and not args.no_peer
+    peer = ctx.peer
     try:
         plan = ShardedDegreeHSD(dg, hops, rank, world, peer=peer)
     except Exception as e:   # symmetric memory unavailable: every rank computes its full row block
@@ -290,13 +311,9 @@ def run_native(args):
         peer = False
         plan = ShardedDegreeHSD(dg, hops, rank, world, peer=False)
     pairs = n * (n - 1) / 2
-    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
-
-    # live FP32 CUDA-core issue peak (the pairwise kernel's roofline denominator)
-    fp32_peak = engine.fp32_issue_peak()
 
     def one_step(ev=None):
-        flush.fill_(1.0)                   # evict the previous step's tables from L2
+        ctx.flush.fill_(1.0)               # evict the previous step's tables from L2
         if ev is not None:
             ev[0].record()
         plan.signatures()
@@ -308,28 +325,26 @@ def run_native(args):
         else:
             plan.distances()
 
-    for _ in range(max(args.warmup, 0)):
+    for _ in range(max(warmup, 0)):
         one_step()
     torch.cuda.synchronize()
     plan.check()
 
-    events = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
-    sampler = ClockSampler(local_rank)
-    barrier()
+    events = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(steps)]
+    sampler = ClockSampler(ctx.local_rank)
+    ctx.barrier()
     torch.cuda.synchronize()
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for k in range(args.steps):
+    for k in range(steps):
         one_step(events[k])
     e1.record()
     torch.cuda.synchronize()
-    barrier()
+    ctx.barrier()
     clocks = sampler.stop()
-    total_ms = max_over_ranks(e0.elapsed_time(e1))
-    ms_per_step = total_ms / args.steps
+    ms_per_step = ctx.max_over_ranks(e0.elapsed_time(e1)) / steps
     value = pairs / (ms_per_step * 1e-3)
-
     bfs_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in events]))
     gather_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in events]))
     pair_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in events]))
@@ -350,12 +365,13 @@ def run_native(args):
     try:
         with open(os.path.join(ROOT, "profiles", "pairwise_ncu_traffic.json")) as f:
             cap = json.load(f)
-        if world == 1 and cap.get("workload") == args.workload:
+        if world == 1 and cap.get("workload") == workload_key:
             traffic = cap["dram_bytes_read"] + cap["dram_bytes_write"]
     except Exception:
         pass
+    fp32_peak = ctx.fp32_peak
     roofline = {
-        "kernel": "pairwise_l1_kernel", "bound": "fp32", "achieved": achieved, "peak": fp32_peak / 1e12,
+        "kernel": "pairwise_l1_v2_kernel", "bound": "fp32", "achieved": achieved, "peak": fp32_peak / 1e12,
         "unit": "TFLOP/s", "frac": achieved / (fp32_peak / 1e12), "traffic": traffic,
         "peak_source": "measured live: hsd_fp32_peak_probe (register-only FADD sub+|.|-accumulate), "
                        "1 flop per lane per clock; MEASURED_PEAKS.json has no FP32 CUDA-core entry",
@@ -367,26 +383,164 @@ def run_native(args):
     sig_rows = plan.sig_all[own, 1:k_alg].double()
     nb1 = dg.n_bins - 1
     sizes = plan.sizes[own].double()
-    sup_max, sup_min = float(dg.support[-1]), float(dg.support[0])
+    sup_max = float(dg.support[-1])
     edges_scanned = float((plan.sig_all[own, 0].double()).sum().item())  # hop 0 expands the source
     for h in range(1, hops):   # rings 1..H-1 are expanded; sum of member degrees = n * mean = n * (max - sum_b CDF*delta)
         mean_deg = sup_max - sig_rows[:, (h - 1) * nb1:h * nb1].sum(1)
         edges_scanned += float((sizes[:, h] * mean_deg).sum().item())
     bfs_bytes = 4.0 * edges_scanned + 4.0 * k_alg * plan.n_src
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peaks = json.load(f)
-    except Exception:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     roofline_bfs = {
         "kernel": "bfs_ring_signature_kernel", "bound": "hbm", "achieved": bfs_bytes / (bfs_ms * 1e-3) / 1e9,
-        "peak": hbm_peak, "unit": "GB/s", "frac": bfs_bytes / (bfs_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
-        "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+        "peak": ctx.hbm_peak, "unit": "GB/s", "frac": bfs_bytes / (bfs_ms * 1e-3) / 1e9 / ctx.hbm_peak, "traffic": None,
+        "peak_source": ctx.hbm_src,
         "bytes_per_launch": bfs_bytes, "ms_per_launch": bfs_ms, "edges_scanned_per_launch": edges_scanned,
-        "note": "CSR (1 MB) and bitmaps are L2/SMEM resident, so HBM fraction is structurally small (SURVEY H4)",
+        "note": "CSR and bitmaps are L2/SMEM resident, so the HBM fraction is structurally small (SURVEY H4)",
     }
+    rec = {"ms_per_step": ms_per_step, "value": value, "pairs": pairs, "peer": peer, "k_alg": k_alg,
+           "n_bins": dg.n_bins, "stage_ms": {"bfs_signature": bfs_ms, "allgather_transpose": gather_ms, "pairwise": pair_ms},
+           "roofline": roofline, "roofline_bfs": roofline_bfs, "clocks": clocks,
+           "launches_per_step": 3 if plan.n_rows else 2}
+    return rec, plan, dg
+
+
+def workload_config(n, hops, world, peer, n_bins):
+    """`config` of the JSON line — identical in the native and the reference arm (the driver compares
+    them); the l2 / symmetric / multi_gpu entries describe how the NATIVE arm runs this workload."""
+    return {"workload": f"barabasi_albert_graph({n}, 5, seed=0), {hops} hops, degree-valued ring signal, full NxN",
+            "n_nodes": n, "hops": hops, "support_bins": int(n_bins), "signature_len": int(1 + hops * (n_bins - 1)),
+            "l2": "native arm: 256 MB buffer written before every step (flush) + each step writes a result > L2",
+            "symmetric": world == 1 or peer, "sharded_over_gpus": world,
+            "multi_gpu": None if world == 1 else (
+                "BFS kernel stores each signature row into every rank's table over NVLink peer memory "
+                "(fused all-gather, no collective); symmetric tiles dealt round-robin to ranks and mirrored "
+                "into the owners' row blocks through peer memory (torch symmetric memory allocations)" if peer else
+                "independent row blocks (every rank computes rows x all columns); one NCCL all-gather")}
+
+
+def extra_c4(ctx):
+    """BASELINE config 4: MultiHSD heat-kernel wavelets, Chebyshev order 30, 4 scales, 50 000 nodes.
+    (i) one 256-column block of hsd_cheb_spmm on rank 0's GPU, with both byte counts; (ii) the whole
+    embedding (all 50k impulse columns + ring reduce), impulse columns sharded over the ranks."""
+    torch = ctx.torch
+    import networkx as nx
+    from hsd_b200 import wavelets as wv
+    from hsd_b200.graph import powerlaw_graph
+    from model import MultiHSD
+    n, order, S, hop, C = 50000, 30, 4, 3, 256
+    g = powerlaw_graph(n, 5, seed=0)
+    lmax = wv.estimate_lmax(g, device=ctx.dev)
+    scales = np.exp(np.linspace(np.log(0.01), np.log(40.0 / lmax), S))
+    coeffs = np.stack([wv.cheby_coefficients(float(s), lmax, order) for s in scales])
+    csr = wv.DeviceCSR(g, ctx.dev)
+    C = wv.column_block(n, S)
+    work = torch.empty((3, n, C), dtype=torch.float64, device=ctx.dev)
+    outb = torch.empty((S, n, C), dtype=torch.float64, device=ctx.dev)
+    times = []
+    for it in range(4):
+        ctx.flush.fill_(1.0)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        wv.cheb_wavelet_block(csr, lmax, coeffs, 0, C, 1e-4 / n, work, outb)
+        b.record()
+        torch.cuda.synchronize()
+        times.append(a.elapsed_time(b))
+    ms = float(np.median(times[1:]))
+    # SURVEY §8(d): every step reads T_{k-1}, T_{k-2}, writes T_k and reads + writes S accumulators;
+    # compulsory: the kernel defers accumulation (3 terms at once), i.e. 174 plane sweeps per block at order 30
+    bytes_survey = order * (8.0 * g.nnz + 4 * (n + 1) + (3 + 2 * S) * 8.0 * n * C)
+    acc_passes = len([k for k in range(2, order + 1) if k % 3 == 2 or k == order])
+    bytes_compulsory = order * (8.0 * g.nnz + 4 * (n + 1) + 3 * 8.0 * n * C) + acc_passes * 2 * S * 8.0 * n * C
+    del work, outb
+    m = MultiHSD(nx.barabasi_albert_graph(n, 5, seed=0), "ba50k", hop, S, device=ctx.dev)
+    m.lmax, m.scales, m.CHEB_ORDER = lmax, scales, order
+    m._rings()
+    torch.cuda.synchronize()
+    ctx.barrier()
+    t0 = time.perf_counter()
+    emb = m.embed_device_sharded(ctx.rank, ctx.world) if ctx.world > 1 else m.embed_device()
+    torch.cuda.synchronize()
+    full_s = ctx.max_over_ranks(time.perf_counter() - t0)
+    rec = {"workload": f"barabasi_albert_graph({n}, 5, seed=0), Chebyshev order {order}, {S} scales in [0.01, 40/lmax], hop {hop}",
+           "kernel": "cheb_step_kernel (FP64)", "block_cols": C, "block_ms": ms,
+           "frac_hbm_survey_bytes": bytes_survey / (ms * 1e-3) / 1e9 / ctx.hbm_peak,
+           "frac_hbm_compulsory_bytes": bytes_compulsory / (ms * 1e-3) / 1e9 / ctx.hbm_peak,
+           "gbs_survey_bytes": bytes_survey / (ms * 1e-3) / 1e9, "gbs_compulsory_bytes": bytes_compulsory / (ms * 1e-3) / 1e9,
+           "hbm_peak_gbs": ctx.hbm_peak, "peak_source": ctx.hbm_src,
+           "full_embedding_s": full_s, "n_gpus": ctx.world,
+           "full_embedding": "all 50k impulse columns + ring [sum, mean] reduce"
+                             + (", impulse columns sharded over the ranks + one all-gather" if ctx.world > 1 else ""),
+           "checksum": float(emb.sum().item())}
+    del m, emb
+    torch.cuda.empty_cache()
+    return rec
+
+
+def extra_c5(ctx):
+    """BASELINE config 5: DynamicHSD on the 100 000-node graph, edges inserted with default_rng(1):
+    time of the incremental update against a from-scratch step (1 GPU: structural_distance_update;
+    N GPUs: structural_distance_update_sharded)."""
+    torch = ctx.torch
+    import networkx as nx
+    from model import DynamicHSD
+    n = 100000
+    out = []
+    for hop, batches in ((4, (5000,)), (2, (5, 5000))):
+        m = DynamicHSD(nx.barabasi_albert_graph(n, 5, seed=0), "ba100k", hop, 1, "wasserstein", signal="degree",
+                       device=ctx.dev)
+
+        def update():
+            if ctx.world > 1:
+                return m.structural_distance_update_sharded(ctx.rank, ctx.world, peer=ctx.peer)
+            return m.structural_distance_update()
+        update()
+        torch.cuda.synchronize()
+        ctx.barrier()
+        if ctx.world == 1:
+            m._D = None
+            m._sig_prev = None
+        else:
+            m._plan = None
+        t0 = time.perf_counter()
+        update()
+        torch.cuda.synchronize()
+        full_ms = ctx.max_over_ranks((time.perf_counter() - t0) * 1e3)
+        rng = np.random.default_rng(1)
+        for k_ins in batches:
+            edges = set()
+            while len(edges) < k_ins:
+                u, v = (int(x) for x in rng.integers(0, n, 2))
+                if u != v and not m.graph.has_edge(u, v):
+                    edges.add((min(u, v), max(u, v)))
+            t0 = time.perf_counter()
+            m.dynamic_add_edges(sorted(edges))
+            edit_ms = (time.perf_counter() - t0) * 1e3
+            ctx.barrier()
+            t0 = time.perf_counter()
+            update()
+            torch.cuda.synchronize()
+            upd_ms = ctx.max_over_ranks((time.perf_counter() - t0) * 1e3)
+            out.append({"hop": hop, "inserted_edges": k_ins, "affected_rows": int(m.last_affected.numel()),
+                        "from_scratch_ms": full_ms, "update_ms": upd_ms, "host_graph_edit_ms": edit_ms})
+        del m
+        torch.cuda.empty_cache()
+    return {"workload": f"barabasi_albert_graph({n}, 5, seed=0) + edge insertions (numpy default_rng(1)), degree signal",
+            "n_gpus": ctx.world, "cases": out,
+            "note": "hop 4: any insertion changes every signature (SURVEY H8), the update is a full recompute; "
+                    "wall-clock ms incl. host-side support check"}
+
+
+def run_native(args):
+    ctx = Ctx(args)
+    torch, dist = ctx.torch, ctx.dist
+    from hsd_b200 import engine
+    from hsd_b200.graph import powerlaw_graph
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
+
+    n, hops = parse_workload(args.workload)
+    g = powerlaw_graph(n, 5, seed=0)       # same deterministic graph on every rank
+    rec, plan, dg = measure_degree_path(ctx, g, hops, args.steps, args.warmup, args.workload)
+    peer = rec["peer"]
+    pairs = rec["pairs"]
 
     # ---- e2e: host buffers in, host matrix out, copies inside the timed region ----
     # N = 1: literally the call a user of the reference makes — the drop-in class,
@@ -413,47 +567,68 @@ def run_native(args):
     e2e_steps = max(3, min(args.steps, 10))
     for _ in range(2):
         e2e_step()
-    barrier()
+    ctx.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         e2e_step()
     torch.cuda.synchronize()
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
-    barrier()
+    e2e_ms = ctx.max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
+    ctx.barrier()
     e2e = {"value": pairs / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": int(pipe.h2d_bytes), "d2h_bytes_per_step": int(pipe.d2h_bytes),
-           "api": api, "cpus_bound_to_gpu_numa_node": numa,
+           "api": api, "cpus_bound_to_gpu_numa_node": ctx.numa,
            "checksum": float(host_out[: min(64, pipe.n_rows)].double().sum().item())}
+    del host_out, pipe
+    if world == 1:
+        del model
+
+    # ---- the other BASELINE.json configs, as sub-records (outside the timed region above) ----
+    extras = {}
+    want = [] if args.no_extras else [x for x in args.extras.split(",") if x]
+    del plan, dg
+    torch.cuda.empty_cache()
+    for key in want:
+        try:
+            if key == "c3" and args.workload != "c3":
+                g3 = powerlaw_graph(100000, 5, seed=0)
+                r3, p3, d3 = measure_degree_path(ctx, g3, 4, 3, 1, "c3")
+                extras["north_star_c3"] = {
+                    "config": workload_config(100000, 4, world, r3["peer"], r3["n_bins"]), "n_gpus": world, "steps": 3, "warmup": 1,
+                    "ms_per_step": r3["ms_per_step"], "value": r3["value"], "unit": UNIT, "stage_ms": r3["stage_ms"],
+                    "frac": r3["roofline"]["frac"], "roofline": r3["roofline"], "roofline_bfs": r3["roofline_bfs"],
+                    "clocks": r3["clocks"]}
+                del p3, d3, g3
+                torch.cuda.empty_cache()
+            elif key == "c4":
+                extras["c4"] = extra_c4(ctx)
+            elif key == "c5":
+                extras["c5"] = extra_c5(ctx)
+        except Exception as e:      # an extra must never take the headline line down with it
+            extras[key] = {"error": f"{type(e).__name__}: {e}"}
+            if world > 1:
+                raise
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        ref = CpuReference(n, hops)
+        ref = CpuReference(n, hops, sample_nodes=CPU_SAMPLE_NODES)
         v, d = ref.step()
         ref.close()
         cpu = {"value": v, "unit": UNIT, "cores": ref.cores, "kind": "port", "sample": ref.describe(d)}
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "metric": METRIC, "value": rec["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": rec["ms_per_step"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"barabasi_albert_graph({n}, 5, seed=0), {hops} hops, degree-valued ring signal, full NxN"
-                                   + (f", row-block sharded over {world} GPUs" if world > 1 else ""),
-                       "n_nodes": n, "hops": hops, "support_bins": dg.n_bins, "signature_len": k_alg,
-                       "l2": "256 MB buffer written before every step (flush) + each step writes a result > L2",
-                       "symmetric": world == 1 or peer,
-                       "multi_gpu": None if world == 1 else (
-                           "BFS kernel stores each signature row into every rank's table over NVLink peer memory "
-                           "(fused all-gather, no collective); symmetric tiles dealt round-robin to ranks and mirrored "
-                           "into the owners' row blocks through peer memory (torch symmetric memory allocations)" if peer else
-                           "independent row blocks (every rank computes rows x all columns); one NCCL all-gather")},
-            "stage_ms": {"bfs_signature": bfs_ms, "allgather_transpose": gather_ms, "pairwise": pair_ms},
-            "roofline": roofline, "roofline_bfs": roofline_bfs, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": int(args.steps * (3 if plan.n_rows else 2)),
-            "clocks": clocks,
+            "config": workload_config(n, hops, world, peer, rec["n_bins"]),
+            "stage_ms": rec["stage_ms"],
+            "roofline": rec["roofline"], "roofline_bfs": rec["roofline_bfs"], "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(args.steps * rec["launches_per_step"]),
+            "clocks": rec["clocks"],
         }
+        line.update(extras)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -468,6 +643,9 @@ def main():
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-peer", action="store_true", help="N>1: independent row blocks instead of peer-memory mirroring")
+    ap.add_argument("--extras", default="c3,c4,c5",
+                    help="other BASELINE.json configs measured after the headline workload, as sub-records of the line")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -34,11 +34,16 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
+def host_sources():
+    """Host-only C++ (the e2e path's multi-threaded mirror): g++, no device code."""
+    return sorted(glob.glob(os.path.join(CSRC, "*.cpp")))
+
+
 def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + \
+    deps = sources() + host_sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + \
         [os.path.join(os.path.dirname(HERE), "include", "hsd_b200.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
@@ -55,13 +60,20 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         cmd = [_nvcc(), *NVCC_FLAGS, "-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
+    gxx = shutil.which("g++") or "g++"
+    for src in host_sources():
+        obj = os.path.join(objdir, os.path.basename(src)[:-4] + "_host.o")
+        cmd = [gxx, "-O3", "-std=c++17", "-fPIC", "-pthread", "-c", src, "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
     for src, p in procs:
         out, _ = p.communicate()
         if verbose or p.returncode != 0:
             print(out)
         if p.returncode != 0:
-            raise RuntimeError(f"nvcc failed on {src}")
-    cmd = [_nvcc(), "-shared", "-o", LIB, *objs]
+            raise RuntimeError(f"compiler failed on {src}")
+    # the arch flag also on the link step: nvcc's device-link stub otherwise targets its default arch (sm_52)
+    cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-Xcompiler", "-pthread"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         print(r.stdout)

@@ -103,3 +103,15 @@ extern "C" int hsd_scatter_symmetric(const float* blk, int64_t blk_ld, int32_t m
     HSD_CUDA_TRY(cudaGetLastError());
     return HSD_OK;
 }
+
+extern "C" int hsd_copy2d_to_host(void* dst_host, int64_t dst_pitch_bytes, const void* src_dev,
+                                  int64_t src_pitch_bytes, int64_t width_bytes, int64_t rows, void* stream) {
+    using namespace hsd;
+    HSD_REQUIRE(dst_host && src_dev, "null pointer");
+    HSD_REQUIRE(width_bytes >= 0 && rows >= 0 && dst_pitch_bytes >= width_bytes && src_pitch_bytes >= width_bytes,
+                "bad window");
+    if (width_bytes == 0 || rows == 0) return HSD_OK;
+    HSD_CUDA_TRY(cudaMemcpy2DAsync(dst_host, (size_t)dst_pitch_bytes, src_dev, (size_t)src_pitch_bytes,
+                                   (size_t)width_bytes, (size_t)rows, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return HSD_OK;
+}

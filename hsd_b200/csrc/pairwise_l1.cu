@@ -432,7 +432,7 @@ pairwise_l1_n64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     }
 }
 
-// ---- v2: persistent CTAs, packed subtract, optional producer warp --------------------------------
+// ---- v2: persistent CTAs, dynamic tile scheduler, packed subtract ---------------------------------
 // (round 2) Same 128 x 128 tile and 8 x 8 register tiles, restructured around what ncu showed in
 // round 1 (profiles/r1_pairwise_notes.md): the kernel was ISSUE-bound — 7.7 % of the issue slots
 // went to instructions that are not FADD and the FMA pipe idled while they issued.
@@ -442,8 +442,8 @@ pairwise_l1_n64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 //    in the shadow of the pipe instead of displacing FADDs;
 //  * persistent CTAs (grid = 2 per SM) walk the tile list; the TMA ring runs ACROSS tiles, so the
 //    next tile's first chunks land while the current tile's 64 + 64 results are being stored;
-//  * PRODW: a ninth warp owns the TMA issue (no compute warp carries the empty-barrier wait and
-//    the two UTMALDG per chunk);
+//  * a dedicated producer warp (288 threads) was built and dropped: at 2 CTAs/SM ptxas then has 96
+//    registers per thread, the 8 x 8 tile spills, and the variant measured 6.5 ms against 5.7 ms;
 //  * the last K chunk runs only its valid rows (groups of 4 k-steps).
 template <int KC_, int STAGES_>
 struct __align__(128) PairSmemV2 {
@@ -509,8 +509,8 @@ __device__ __forceinline__ void pair_kstep(const float* __restrict__ arow, const
     }
 }
 
-template <int KC_, int STAGES_, int UNROLL, bool PACKED, bool PRODW>
-__global__ void __launch_bounds__(PRODW ? PAIR_THREADS + 32 : PAIR_THREADS, 2)
+template <int KC_, int STAGES_, int UNROLL, bool PACKED>
+__global__ void __launch_bounds__(PAIR_THREADS, 2)
 pairwise_l1_v2_kernel(const __grid_constant__ CUtensorMap tmap, const PairArgs p) {
     using Smem = PairSmemV2<KC_, STAGES_>;
     constexpr uint32_t BYTES = 2u * KC_ * TILE * sizeof(float);
@@ -571,15 +571,8 @@ pairwise_l1_v2_kernel(const __grid_constant__ CUtensorMap tmap, const PairArgs p
         if (++ps == STAGES_) { ps = 0; pph ^= 1u; }
     };
 
-    if (PRODW) {
-        if (tid >= PAIR_THREADS) {
-            if (tid == PAIR_THREADS)
-                while (!pdone) produce_one();
-            return;
-        }
-    } else if (tid == 0) {
+    if (tid == 0)
         for (int n = 0; n < p.lookahead; ++n) produce_one();
-    }
 
     // ===== consumers: 16 x 16 threads, each 8 x 8 outputs (2 x 2 blocks of 4 x 4) =====
     const int tx = tid & 15, ty = tid >> 4;
@@ -595,7 +588,7 @@ pairwise_l1_v2_kernel(const __grid_constant__ CUtensorMap tmap, const PairArgs p
     for (;;) {
         int t = 0;
         for (int c = 0; c < k_chunks; ++c) {
-            if (!PRODW && tid == 0) produce_one();
+            if (tid == 0) produce_one();
             if (!ready) mbar_wait(smem_u32(&sm.full[s]), ph);
             if (c == 0) {
                 t = *((volatile int*)&sm.tile_of_stage[s]);
@@ -753,13 +746,13 @@ static V2Config v2_config() {
 // different streams (up to 64 in flight per device) do not share a counter.
 __device__ unsigned int g_tile_counters[64];
 
-template <int KC_, int STAGES_, bool PACKED, bool PRODW, int UNROLL = 8>
+template <int KC_, int STAGES_, bool PACKED, int UNROLL>
 static int launch_v2(const CUtensorMap& tmap, const PairArgs& a, cudaStream_t stream, int sms) {
-    auto kern = pairwise_l1_v2_kernel<KC_, STAGES_, UNROLL, PACKED, PRODW>;
+    auto kern = pairwise_l1_v2_kernel<KC_, STAGES_, UNROLL, PACKED>;
     const int smem = (int)sizeof(PairSmemV2<KC_, STAGES_>);
     HSD_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int grid = (int)std::min<long long>(a.n_tiles, 2ll * sms);
-    kern<<<grid, PRODW ? PAIR_THREADS + 32 : PAIR_THREADS, smem, stream>>>(tmap, a);
+    kern<<<grid, PAIR_THREADS, smem, stream>>>(tmap, a);
     HSD_CUDA_TRY(cudaGetLastError());
     return HSD_OK;
 }
@@ -808,15 +801,9 @@ static int launch_pairwise_v2(const V2Config& c, const float* sigT, int32_t k_us
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 #define HSD_V2_CASE(KC_, ST_)                                                                        \
     if (c.kc == KC_ && c.stages == ST_) {                                                            \
-        if (c.packed) {                                                                              \
-            if (c.unroll == 2) return launch_v2<KC_, ST_, true, false, 2>(tmap, a, stream, sms);     \
-            if (c.unroll == 4) return launch_v2<KC_, ST_, true, false, 4>(tmap, a, stream, sms);     \
-            if (c.unroll == 16) return launch_v2<KC_, ST_, true, false, 16>(tmap, a, stream, sms);   \
-            return launch_v2<KC_, ST_, true, false, 8>(tmap, a, stream, sms);                        \
-        }                                                                                            \
-        if (c.unroll == 2) return launch_v2<KC_, ST_, false, false, 2>(tmap, a, stream, sms);        \
-        if (c.unroll == 4) return launch_v2<KC_, ST_, false, false, 4>(tmap, a, stream, sms);        \
-        return launch_v2<KC_, ST_, false, false, 8>(tmap, a, stream, sms);                           \
+        if (c.packed && c.unroll == 16) return launch_v2<KC_, ST_, true, 16>(tmap, a, stream, sms);  \
+        if (c.packed) return launch_v2<KC_, ST_, true, 8>(tmap, a, stream, sms);                     \
+        return launch_v2<KC_, ST_, false, 8>(tmap, a, stream, sms);                                  \
     }
     HSD_V2_CASE(16, 4)
     HSD_V2_CASE(32, 3)

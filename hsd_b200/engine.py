@@ -318,7 +318,16 @@ class HostDegreePipeline:
     dominant cost at N = 20k (1.6 GB) — overlaps the kernels."""
 
     def __init__(self, g: CSRGraph, hops: int, empty: str = "raise", device=None,
-                 row0: int = 0, n_rows: Optional[int] = None, n_chunks: int = 8):
+                 row0: int = 0, n_rows: Optional[int] = None, n_chunks: int = 8,
+                 host_mirror: Optional[bool] = None, host_threads: Optional[int] = None):
+        """host_mirror (full matrices only; opt-in, HSD_E2E_HOST_MIRROR=1): ship only the upper
+        trapezoid of every row panel over PCIe (0.86-0.95 GB instead of 1.6 GB at N = 20k) and let
+        `host_threads` CPU threads mirror it into the rows below (hsd_mirror_upper_to_lower_host)
+        while later panels are still in flight.  Off by default: on the B200 boxes of this pool
+        (16 vCPUs, ~60 GB/s of host memory traffic) the mirror alone takes 26 ms, longer than
+        the 15 ms of PCIe time it saves (measured 32.7 ms/step against 30.2 ms for the full copy,
+        gpurun_out/r2_e2e_a.log -> profiles/r2_e2e_notes.md); it pays on hosts whose cores can move
+        > 110 GB/s."""
         self.dev = device or require_cuda()
         self.g, self.hops, self.empty = g, hops, empty
         o = g.degree_order()
@@ -341,10 +350,19 @@ class HostDegreePipeline:
         self.out_rows_idx = torch.arange(self.n, dtype=torch.int32, device=self.dev)
         self.status = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.D = torch.empty((self.n_rows, self.n), dtype=torch.float32, device=self.dev)
-        self.d2h_bytes = self.n_rows * self.n * 4
         self.copy_stream = torch.cuda.Stream(device=self.dev)
         self.panels = self._plan_panels(n_chunks)
         self.launches_per_step = 2 + len(self.panels)
+        import os
+        if host_mirror is None:
+            host_mirror = os.environ.get("HSD_E2E_HOST_MIRROR", "0") == "1"
+        self.host_mirror = bool(host_mirror) and self.full
+        avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        self.host_threads = max(1, min(int(host_threads or os.environ.get("HSD_E2E_HOST_THREADS", 0) or avail), 64))
+        if self.host_mirror:     # each row panel [p0, p0+pr) ships columns [p0, N) only
+            self.d2h_bytes = sum(pr * (self.n - p0) * 4 for p0, pr in self.panels)
+        else:
+            self.d2h_bytes = self.n_rows * self.n * 4
 
     def _plan_panels(self, n_chunks: int):
         """Row panels (multiples of the 128-row tile).  Symmetric mode: tile row I costs
@@ -373,6 +391,9 @@ class HostDegreePipeline:
             self.dev_in[k].copy_(v, non_blocking=True)
         d = self.dev_in
         self.status.zero_()
+        arrived = []
+        if out.stride(1) != 1:
+            raise ValueError("out must be row-major")
         ensure_bfs_workspace(self.n, self.dev)
         check(lib.hsd_ring_signature_degree(
             _ptr(d["rowptr"]), _ptr(d["col"]), self.n, _ptr(d["new_of"]), _ptr(self.out_rows_idx), self.n,
@@ -393,8 +414,22 @@ class HostDegreePipeline:
             ev = torch.cuda.Event()
             ev.record(cur)
             self.copy_stream.wait_event(ev)
-            with torch.cuda.stream(self.copy_stream):
-                out[p0:p0 + pr].copy_(self.D[p0:p0 + pr], non_blocking=True)
+            if self.host_mirror:
+                # upper trapezoid of the panel only: rows [p0, p0+pr) x columns [p0, N)
+                check(lib.hsd_copy2d_to_host(out[p0:, p0:].data_ptr(), out.stride(0) * 4,
+                                             self.D[p0:, p0:].data_ptr(), self.D.stride(0) * 4,
+                                             (self.n - p0) * 4, pr, self.copy_stream.cuda_stream))
+                done = torch.cuda.Event()
+                done.record(self.copy_stream)
+                arrived.append((done, p0, pr))
+            else:
+                with torch.cuda.stream(self.copy_stream):
+                    out[p0:p0 + pr].copy_(self.D[p0:p0 + pr], non_blocking=True)
+        for done, p0, pr in arrived:
+            # the host cores fill D[j][i] = D[i][j] below the panel while later panels are still crossing PCIe
+            done.synchronize()
+            check(lib.hsd_mirror_upper_to_lower_host(out.data_ptr(), out.stride(0), self.n, p0, p0 + pr,
+                                                     self.host_threads))
         self.copy_stream.synchronize()
         if self.empty == "raise" and int(self.status.item()) & 1:
             raise EmptyRingError("Distribution can't be empty.")

@@ -272,6 +272,19 @@ int hsd_topk_rows(const float* D, int64_t ld, int32_t n_rows, int32_t n_cols, in
                   int32_t self_col0, const uint32_t* col_mask, int32_t* idx_out, float* val_out,
                   void* stream);
 
+/* ---- e2e path: ship each unordered pair once, mirror on the host --------------------
+ * The reference returns the dense symmetric ndarray (model/HSD.py:100-114, dist_mat[i,j] =
+ * dist_mat[j,i]).  Over PCIe the matrix is the e2e bottleneck, so the host pipeline copies only
+ * the upper trapezoid of every finished row panel (hsd_copy2d_to_host: one cudaMemcpy2DAsync,
+ * rows x width_bytes window, both pitches in bytes; dst_host should be pinned) and the host cores
+ * fill the rows below it: hsd_mirror_upper_to_lower_host sets D[j][i] = D[i][j] for
+ * row_begin <= i < row_end, i < j < n (HOST pointers; row_begin a multiple of 64; blocked
+ * transposes on n_threads threads, AVX2 + streaming stores when the CPU has them). */
+int hsd_copy2d_to_host(void* dst_host, int64_t dst_pitch_bytes, const void* src_dev, int64_t src_pitch_bytes,
+                       int64_t width_bytes, int64_t rows, void* stream);
+int hsd_mirror_upper_to_lower_host(float* D_host, int64_t ld, int32_t n, int32_t row_begin,
+                                   int32_t row_end, int32_t n_threads);
+
 /* ---- measurement helper: FP32 CUDA-core issue peak ---------------------------
  * Runs a register-only FADD kernel (same sub + |.|-accumulate instruction mix as
  * the pairwise inner loop, no memory) and returns lane-ops in *lane_ops; the

@@ -297,3 +297,19 @@ def test_calculate_distance_metric_names_and_exceptions():
     with pytest.raises(TypeError):
         calculate_distance(p, q, None)
     assert calculate_distance([], [], "l1") == 0.0
+
+
+@pytest.mark.parametrize("n,panels,threads", [(1000, [(0, 1000)], 3), (4099, [(0, 256), (256, 768), (1024, 3075)], 8),
+                                               (130, [(0, 128), (128, 2)], 1)])
+def test_host_mirror_completes_the_symmetric_matrix(n, panels, threads):
+    """hsd_mirror_upper_to_lower_host (the opt-in e2e path that ships each unordered pair once):
+    panel by panel, D[j][i] = D[i][j] below the panel; entries on and above the diagonal untouched."""
+    from hsd_b200._lib import check, lib
+    rng = np.random.default_rng(n)
+    U = np.triu(rng.random((n, n), dtype=np.float32))
+    D = U.copy()
+    D[np.tril_indices(n, -1)] = -1.0
+    for p0, pr in panels:
+        check(lib.hsd_mirror_upper_to_lower_host(D.ctypes.data, n, n, p0, p0 + pr, threads))
+    assert np.array_equal(D, U + np.triu(U, 1).T)
+    assert lib.hsd_mirror_upper_to_lower_host(D.ctypes.data, n, n, 5, 64, 1) == -1     # panels start on 64-row boundaries

@@ -496,12 +496,13 @@ def extra_c5(ctx):
         torch.cuda.synchronize()
         ctx.barrier()
         if ctx.world == 1:
-            m._D = None
+            m._D = None          # forget the previous matrix: the next call is a from-scratch step
             m._sig_prev = None
+            t0 = time.perf_counter()
+            update()
         else:
-            m._plan = None
-        t0 = time.perf_counter()
-        update()
+            t0 = time.perf_counter()
+            m._plan.step()       # from scratch on the existing plan (buffers and peer mappings kept)
         torch.cuda.synchronize()
         full_ms = ctx.max_over_ranks((time.perf_counter() - t0) * 1e3)
         rng = np.random.default_rng(1)
@@ -529,6 +530,57 @@ def extra_c5(ctx):
                     "wall-clock ms incl. host-side support check"}
 
 
+def _time_e2e(ctx, step, steps, pairs, pipe, api, host_out):
+    torch = ctx.torch
+    for _ in range(2):
+        step()
+    ctx.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    torch.cuda.synchronize()
+    mine_ms = (time.perf_counter() - t0) * 1e3 / steps
+    e2e_ms = ctx.max_over_ranks(mine_ms)
+    ctx.barrier()
+    return {"value": pairs / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+            "h2d_bytes_per_step": int(pipe.h2d_bytes), "d2h_bytes_per_step": int(pipe.d2h_bytes),
+            "d2h_gbs_this_rank": pipe.d2h_bytes / (mine_ms * 1e-3) / 1e9,
+            "d2h_gbs_all_ranks": ctx.world * pipe.d2h_bytes / (e2e_ms * 1e-3) / 1e9,
+            "api": api, "cpus_bound_to_gpu_numa_node": ctx.numa,
+            "note": "PCIe/host-memory bound: the float32 result (N^2 x 4 B over all ranks) crosses PCIe inside the timed "
+                    "region; kernels are ~20 % of it at N = 1 and overlap the copies",
+            "checksum": float(host_out[: min(64, pipe.n_rows)].double().sum().item())}
+
+
+def run_e2e_single(ctx, n, hops, args, pairs):
+    """N = 1: literally the call a user of the reference makes — the drop-in class,
+    HSD.calculate_structural_distance(scale, out=<pinned host buffer>) -> engine.HostDegreePipeline:
+    pinned host CSR -> H2D -> kernels -> D2H of finished row panels overlapped with the panels still computing."""
+    torch = ctx.torch
+    import networkx as nx
+    from model import HSD
+    model = HSD(nx.barabasi_albert_graph(n, 5, seed=0), f"ba{n}", 0, hops, "wasserstein", signal="degree")
+    host_out = torch.empty((n, n), dtype=torch.float32).pin_memory()
+
+    def step():
+        model.calculate_structural_distance(0.0, out=host_out)   # synchronises: the result is in host memory
+    step()
+    api = "model.HSD(graph, name, 0, hop, metric, signal='degree').calculate_structural_distance(0.0, out=pinned)"
+    return _time_e2e(ctx, step, max(3, min(args.steps, 10)), pairs, model._host_pipe, api, host_out)
+
+
+def run_e2e_sharded(ctx, g, hops, plan, args, pairs):
+    """N > 1: every rank runs the same host pipeline for its row shard (rows x all columns, panels
+    streamed out while later panels compute)."""
+    torch = ctx.torch
+    from hsd_b200 import engine
+    pipe = engine.HostDegreePipeline(g, hops, device=ctx.dev, row0=plan.row0, n_rows=plan.n_rows)
+    host_out = torch.empty((pipe.n_rows, g.n), dtype=torch.float32).pin_memory()
+    api = "hsd_b200.engine.HostDegreePipeline.run on each rank's row shard (what HSD.calculate_structural_distance(out=) calls)"
+    return _time_e2e(ctx, lambda: pipe.run(host_out), max(3, min(args.steps, 10)), pairs, pipe, api, host_out)
+
+
 def run_native(args):
     ctx = Ctx(args)
     torch, dist = ctx.torch, ctx.dist
@@ -546,43 +598,12 @@ def run_native(args):
     # N = 1: literally the call a user of the reference makes — the drop-in class,
     # HSD.calculate_structural_distance(scale, out=<pinned host buffer>) — which runs
     # engine.HostDegreePipeline.  N > 1: every rank runs the same pipeline for its row shard.
-    if world == 1:
-        import networkx as nx
-        from model import HSD
-        model = HSD(nx.barabasi_albert_graph(n, 5, seed=0), f"ba{n}", 0, hops, "wasserstein", signal="degree")
-        host_out = torch.empty((n, n), dtype=torch.float32).pin_memory()
-
-        def e2e_step():
-            model.calculate_structural_distance(0.0, out=host_out)   # synchronises: result is in host memory
-        e2e_step()
-        pipe = model._host_pipe
-        api = "model.HSD(graph, name, 0, hop, metric, signal='degree').calculate_structural_distance(0.0, out=pinned)"
+    if args.no_e2e:
+        e2e = None
+    elif world == 1:
+        e2e = run_e2e_single(ctx, n, hops, args, pairs)
     else:
-        pipe = engine.HostDegreePipeline(g, hops, device=dev, row0=plan.row0, n_rows=plan.n_rows)
-        host_out = torch.empty((pipe.n_rows, n), dtype=torch.float32).pin_memory()
-
-        def e2e_step():
-            pipe.run(host_out)
-        api = "hsd_b200.engine.HostDegreePipeline.run on each rank's row shard (what HSD.calculate_structural_distance(out=) calls)"
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
-        e2e_step()
-    ctx.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    torch.cuda.synchronize()
-    e2e_ms = ctx.max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
-    ctx.barrier()
-    e2e = {"value": pairs / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-           "h2d_bytes_per_step": int(pipe.h2d_bytes), "d2h_bytes_per_step": int(pipe.d2h_bytes),
-           "api": api, "cpus_bound_to_gpu_numa_node": ctx.numa,
-           "checksum": float(host_out[: min(64, pipe.n_rows)].double().sum().item())}
-    del host_out, pipe
-    if world == 1:
-        del model
-
+        e2e = run_e2e_sharded(ctx, g, hops, plan, args, pairs)
     # ---- the other BASELINE.json configs, as sub-records (outside the timed region above) ----
     extras = {}
     want = [] if args.no_extras else [x for x in args.extras.split(",") if x]
@@ -646,6 +667,7 @@ def main():
     ap.add_argument("--extras", default="c3,c4,c5",
                     help="other BASELINE.json configs measured after the headline workload, as sub-records of the line")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg (NVLink byte-count runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

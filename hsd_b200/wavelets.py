@@ -6,8 +6,10 @@ Chebyshev approximation applied to one unit impulse at a time, or a dense
 ``eigh``; then the threshold ``x if x > coeff/N else 0``.
 
 Here the Chebyshev path is one CSR SpMM kernel over a block of impulse columns
-(hsd_cheb_spmm); the exact path uses the vendor eigensolver through torch
-(cuSOLVER, FP64) — a plain library call, it is the step *before* the hot path.
+(hsd_cheb_spmm); the exact path takes the eigendecomposition from the vendor solver
+through torch (cuSOLVER, FP64 — the step *before* the hot path, LAPACK in the
+reference) and forms U diag(exp(-s lambda)) U^T with the threshold in one fused
+kernel (hsd_exact_wavelets).
 """
 from __future__ import annotations
 
@@ -143,10 +145,16 @@ def cheb_wavelets_dense(csr: DeviceCSR, scale: float, lmax: float, order: int,
 
 def exact_wavelets_dense(L: torch.Tensor, scale: float, thr_coeff: Optional[float],
                          eig=None) -> torch.Tensor:
-    """U diag(exp(-s lambda)) U^T then threshold (model/HSD.py:61-66), FP64 on device."""
+    """U diag(exp(-s lambda)) U^T then threshold (model/HSD.py:61-66), FP64 on device: ONE fused
+    kernel (hsd_exact_wavelets: scaling, product, threshold, symmetric mirror) — the un-thresholded
+    N x N product is never materialised.  Only the eigendecomposition is a vendor call (cuSOLVER
+    through torch.linalg.eigh), as numpy's LAPACK eigh is in the reference."""
     lam, U = eig if eig is not None else torch.linalg.eigh(L)
-    psi = (U * torch.exp(-scale * lam)[None, :]) @ U.t()
-    if thr_coeff is not None:
-        thr = thr_coeff * 1.0 / L.shape[0]
-        psi = torch.where(psi > thr, psi, torch.zeros((), dtype=psi.dtype, device=psi.device))
+    n = L.shape[0]
+    U = U.contiguous()
+    lam = lam.contiguous()
+    psi = torch.empty((n, n), dtype=torch.float64, device=U.device)
+    thr = 0.0 if thr_coeff is None else thr_coeff * 1.0 / n
+    check(lib.hsd_exact_wavelets(engine._ptr(U), U.stride(0), engine._ptr(lam), n, float(scale), float(thr),
+                                 0 if thr_coeff is None else 1, engine._ptr(psi), psi.stride(0), engine._stream()))
     return psi

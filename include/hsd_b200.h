@@ -230,6 +230,17 @@ int hsd_cheb_spmm(const int32_t* rowptr, const int32_t* col, int32_t n_nodes,
                   int32_t col0, int32_t n_cols, double threshold,
                   double* work, double* out, void* stream);
 
+/* ---- exact heat-kernel wavelets from an eigendecomposition, threshold fused ------
+ * Replaces model/HSD.py:61-66 / model/GraphWave.py:42-49 (two dense np.dot + np.vectorize):
+ *   out[i][j] = sum_k U[i][k] exp(-scale lam[k]) U[j][k], then (apply_threshold != 0)
+ *   out = out > threshold ? out : 0.  U double[n][ldu] holds the eigenvectors as COLUMNS (what
+ * numpy / torch eigh return), lam double[n].  One FP64 kernel; only tiles on or above the diagonal
+ * are computed and each is stored mirrored, so out is exactly symmetric and the un-thresholded
+ * product is never materialised.  (The eigendecomposition stays on the vendor solver.) */
+int hsd_exact_wavelets(const double* U, int64_t ldu, const double* lam, int32_t n_nodes,
+                       double scale, double threshold, int32_t apply_threshold, double* out,
+                       int64_t ld_out, void* stream);
+
 /* y = L x, L = D - A from the CSR (unit weights, self-loops cancel), one FP64 vector.  The
  * building block of the lmax estimate that replaces pygsp's Graph.estimate_lmax (ARPACK;
  * call sites model/HSD.py:51, model/multiscale_HSD.py:28) with a power iteration on the device. */

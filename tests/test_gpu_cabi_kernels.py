@@ -299,3 +299,29 @@ def test_topk_long_rows_with_column_mask(n_cols, levels):
         order = sorted((int(j) for j in cols if j != r), key=lambda j: (D[r, j], j))[:k]
         assert idx[r].tolist() == order
         assert np.array_equal(val[r], D[r, order])
+
+
+@pytest.mark.parametrize("n", [1, 63, 130, 399])
+def test_exact_wavelets_fused_kernel(n):
+    """hsd_exact_wavelets = U diag(exp(-s lambda)) U^T with the threshold of model/HSD.py:65 fused,
+    against the reference's own two np.dot products (model/HSD.py:61-63) on the host."""
+    import torch
+    from hsd_b200 import wavelets as wv
+    rng = np.random.default_rng(n)
+    A = (rng.random((n, n)) < 0.1).astype(np.float64)
+    A = np.triu(A, 1)
+    A = A + A.T
+    L = np.diag(A.sum(1)) - A
+    lam, U = np.linalg.eigh(L)
+    for scale, coeff in ((0.7, 1e-4), (3.0, None)):
+        ref = np.dot(np.dot(U, np.diag(np.exp(-1 * scale * lam))), np.transpose(U))
+        eig = (torch.from_numpy(lam).cuda(), torch.from_numpy(U).cuda())
+        got = wv.exact_wavelets_dense(torch.from_numpy(L).cuda(), scale, coeff, eig).cpu().numpy()
+        assert np.array_equal(got, got.T)
+        if coeff is not None:
+            thr = coeff / n
+            keep = np.abs(ref - thr) > 1e-12          # entries within rounding of the threshold may flip
+            ref = np.where(ref > thr, ref, 0.0)
+            np.testing.assert_allclose(got[keep], ref[keep], rtol=1e-11, atol=1e-14)
+        else:
+            np.testing.assert_allclose(got, ref, rtol=1e-11, atol=1e-14)

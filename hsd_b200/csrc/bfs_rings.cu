@@ -123,43 +123,70 @@ __device__ __forceinline__ void bfs_one_source(const BfsArgs& p, const int sidx,
         for (int r0 = 0; r0 < n_cur; r0 += FL_CAP) {
             const int m = min(FL_CAP, n_cur - r0);
             // ---- compact ring members with rank in [r0, r0 + m) into the frontier list ----
-            for (int w = tid; w < nw; w += THREADS) {
-                uint32_t bits = F[w];
-                if (!bits) continue;
-                int pos = (int)P[w] - r0;
-                if (pos >= m || pos + __popc(bits) <= 0) continue;
-                while (bits) {
-                    const int v = (w << 5) + __ffs(bits) - 1;
-                    bits &= bits - 1;
-                    if (pos >= 0 && pos < m) {
-                        const int e0 = __ldg(p.rowptr + v);
-                        fl_start[pos] = e0;
-                        fl_eo[pos] = __ldg(p.rowptr + v + 1) - e0;   // degree for now
+            // RANK-balanced: every thread takes an equal, contiguous run of ranks, finds the word
+            // that holds its first rank by binary search on the prefix popcounts and walks the bits
+            // from there.  (Word-balanced compaction — round 1 — gave the threads that own the top
+            // words of the degree-ordered bitmap, where every ring has all its hubs, up to 32
+            // dependent row-pointer loads while the rest had none: 26 % of all stall samples at C3
+            // were on the barrier behind them.)  The run's row pointers are loaded back to back and
+            // the degrees stay in registers for the scan: one barrier less per round.
+            const int cpr = (m + THREADS - 1) / THREADS;          // ranks per thread, <= FL_PER_THREAD
+            const int p0 = min(tid * cpr, m), p1 = min(p0 + cpr, m);
+            int st[FL_PER_THREAD], loc[FL_PER_THREAD];
+            int sum = 0;
+            {
+                int vs[FL_PER_THREAD];
+                if (p0 < p1) {
+                    const int r = r0 + p0;
+                    int lo = 0, hi = nw;                         // last w with P[w] <= r holds rank r
+                    while (hi - lo > 1) {
+                        const int mid = (lo + hi) >> 1;
+                        if ((int)P[mid] <= r) lo = mid; else hi = mid;
                     }
-                    ++pos;
+                    int w = lo;
+                    uint32_t bits = F[w];
+                    for (int skip = r - (int)P[w]; skip > 0; --skip) bits &= bits - 1;
+#pragma unroll
+                    for (int q = 0; q < FL_PER_THREAD; ++q) {
+                        if (p0 + q < p1) {
+                            while (!bits) bits = F[++w];
+                            vs[q] = (w << 5) + __ffs(bits) - 1;
+                            bits &= bits - 1;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < FL_PER_THREAD; ++q) {        // independent loads: all in flight together
+                    st[q] = 0;
+                    loc[q] = 0;
+                    if (p0 + q < p1) {
+                        st[q] = __ldg(p.rowptr + vs[q]);
+                        loc[q] = __ldg(p.rowptr + vs[q] + 1);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < FL_PER_THREAD; ++q) {
+                    loc[q] -= st[q];                              // degree
+                    sum += loc[q];
                 }
             }
-            __syncthreads();
             // ---- exclusive scan of the degrees -> edge offsets ----
-            int loc[FL_PER_THREAD];
-            int sum = 0;
-#pragma unroll
-            for (int q = 0; q < FL_PER_THREAD; ++q) {
-                const int i = tid * FL_PER_THREAD + q;
-                loc[q] = (i < m) ? fl_eo[i] : 0;
-                sum += loc[q];
-            }
             int total;
             int run = block_exclusive_scan<THREADS>(sum, warp_tot, &total);   // syncs inside
 #pragma unroll
             for (int q = 0; q < FL_PER_THREAD; ++q) {
-                const int i = tid * FL_PER_THREAD + q;
-                if (i < m) fl_eo[i] = run;
+                if (p0 + q < p1) {
+                    fl_start[p0 + q] = st[q];
+                    fl_eo[p0 + q] = run;
+                }
                 run += loc[q];
             }
             if (tid == 0) fl_eo[m] = total;
             __syncthreads();
             // ---- each thread walks an equal contiguous share of the `total` edges ----
+            // 16-byte groups of column indices, software-pipelined: the next group of this list (or
+            // the first group of the next frontier node's list) is requested before the current
+            // group's four bitmap tests, so a thread always has one L2 round trip in flight.
             const int share = (total + THREADS - 1) / THREADS;
             int e = min(tid * share, total);
             const int e_hi = min(e + share, total);
@@ -170,22 +197,34 @@ __device__ __forceinline__ void bfs_one_source(const BfsArgs& p, const int sidx,
                     if (fl_eo[mid] <= e) lo = mid; else hi = mid;
                 }
                 int k = lo;
-                while (e < e_hi) {
-                    const int eo_k = fl_eo[k];
-                    const int k_end = min(fl_eo[k + 1], e_hi);
-                    const int base = fl_start[k] - eo_k;     // CSR index = base + e
-                    int i = base + e;
-                    const int i_end = base + k_end;
-                    // aligned 16-byte groups; entries outside [i, i_end) are masked
-                    for (int g = i & ~3; g < i_end; g += 4) {
-                        const int4 c = __ldg(reinterpret_cast<const int4*>(p.col + g));
-                        if (g >= i && g < i_end) visit_neighbor(c.x, S);
-                        if (g + 1 >= i && g + 1 < i_end) visit_neighbor(c.y, S);
-                        if (g + 2 >= i && g + 2 < i_end) visit_neighbor(c.z, S);
-                        if (g + 3 >= i && g + 3 < i_end) visit_neighbor(c.w, S);
+                int k_end = min(fl_eo[k + 1], e_hi);
+                int i = fl_start[k] + (e - fl_eo[k]);            // CSR index range [i, i_end) of this list
+                int i_end = i + (k_end - e);
+                int g = i & ~3;
+                int4 c = __ldg(reinterpret_cast<const int4*>(p.col + g));
+                for (;;) {
+                    // what comes after group g: the next group of this list, else the next list
+                    int ng = g + 4, ni = i, ni_end = i_end, nk_end = k_end;
+                    bool more = true;
+                    if (ng >= i_end) {
+                        if (k_end < e_hi) {
+                            ++k;
+                            nk_end = min(fl_eo[k + 1], e_hi);
+                            ni = fl_start[k];
+                            ni_end = ni + (nk_end - k_end);
+                            ng = ni & ~3;
+                        } else {
+                            more = false;
+                        }
                     }
-                    e = k_end;
-                    ++k;
+                    int4 cn = c;
+                    if (more) cn = __ldg(reinterpret_cast<const int4*>(p.col + ng));
+                    if (g >= i && g < i_end) visit_neighbor(c.x, S);
+                    if (g + 1 >= i && g + 1 < i_end) visit_neighbor(c.y, S);
+                    if (g + 2 >= i && g + 2 < i_end) visit_neighbor(c.z, S);
+                    if (g + 3 >= i && g + 3 < i_end) visit_neighbor(c.w, S);
+                    if (!more) break;
+                    c = cn; g = ng; i = ni; i_end = ni_end; k_end = nk_end;
                 }
             }
             __syncthreads();

@@ -179,7 +179,10 @@ class DynamicHSD(MultiHSD):
         reusable = (plan is not None and plan.world == world and plan.rank == rank and plan.dg.n == dg.n
                     and plan.hops == self.hop and np.array_equal(plan.dg.support, dg.support))
         if not reusable:
-            self._plan = plan = ShardedDegreeHSD(dg, self.hop, rank, world, group=group, empty=self.empty, peer=peer)
+            # a changed support (a new distinct degree) changes the signature length, not the result block:
+            # the new plan takes over the old one's symmetric-memory allocations where they still fit
+            self._plan = plan = ShardedDegreeHSD(dg, self.hop, rank, world, group=group, empty=self.empty, peer=peer,
+                                                 reuse=plan)
             blk = plan.step()
             self.last_affected = torch.arange(dg.n, device=dg.rowptr.device)
         else:

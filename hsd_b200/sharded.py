@@ -73,7 +73,7 @@ class ShardedDegreeHSD:
 
     def __init__(self, dg: engine.DeviceGraph, hops: int, rank: int = 0, world: int = 1,
                  group=None, empty: str = "raise", peer: bool = False, peer_blocks=None,
-                 peer_tables=None):
+                 peer_tables=None, reuse: "ShardedDegreeHSD" = None):
         """peer=True (world > 1): the result blocks are allocated as symmetric memory and mapped
         into every rank over NVLink; the pairwise kernel then computes each symmetric tile once
         in the whole job and stores its mirror straight into the owner's block
@@ -82,7 +82,11 @@ class ShardedDegreeHSD:
         produces into all ranks' copies (hsd_ring_signature_degree_allgather), so no collective is
         issued at all — only two barriers per step.
         peer_blocks / peer_tables: lists of `world` local tensors standing in for the peers'
-        result blocks / signature tables (single-GPU emulation in the tests)."""
+        result blocks / signature tables (single-GPU emulation in the tests).
+        reuse: a previous plan of the same node count / rank / world / peer mode whose symmetric-memory
+        allocations (result block, and the signature table when the new one fits its capacity) are
+        taken over instead of allocated and rendezvous-ed again — what an incremental update needs
+        when an insertion adds a distinct degree and every signature changes length."""
         self.dg, self.hops, self.rank, self.world, self.group, self.empty = dg, hops, rank, world, group, empty
         n = dg.n
         dev = dg.rowptr.device
@@ -100,9 +104,20 @@ class ShardedDegreeHSD:
         elif self.peer and peer_blocks is None:
             import torch.distributed as dist
             import torch.distributed._symmetric_memory as symm_mem
-            self.sig_all = symm_mem.empty((world * self.per, self.ld), dtype=torch.float32, device=dev)
-            self.sig_all.zero_()
-            self.sig_symm = symm_mem.rendezvous(self.sig_all, group if group is not None else dist.group.WORLD)
+            need = world * self.per * self.ld
+            ok = (reuse is not None and reuse.peer and reuse.sig_symm is not None and reuse.world == world
+                  and reuse.rank == rank and reuse.dg.n == n and getattr(reuse, "_sig_flat", None) is not None
+                  and reuse._sig_flat.numel() >= need)
+            if ok:
+                self._sig_flat, self.sig_symm = reuse._sig_flat, reuse.sig_symm
+                dist.barrier(group=group)  # nobody is still storing rows of the old layout into it
+            else:
+                # capacity for a few more distinct degrees per hop than the graph has now
+                cap = world * self.per * engine.roundup(self.k_used + 16 * hops, 4)
+                self._sig_flat = symm_mem.empty((cap,), dtype=torch.float32, device=dev)
+                self.sig_symm = symm_mem.rendezvous(self._sig_flat, group if group is not None else dist.group.WORLD)
+            self._sig_flat.zero_()
+            self.sig_all = self._sig_flat[:need].view(world * self.per, self.ld)
             self.sig_peer_ptrs = torch.tensor([int(p) for r, p in enumerate(self.sig_symm.buffer_ptrs) if r != rank],
                                               dtype=torch.int64, device=dev)
             torch.cuda.synchronize(dev)
@@ -127,8 +142,12 @@ class ShardedDegreeHSD:
         elif self.peer:
             import torch.distributed as dist
             import torch.distributed._symmetric_memory as symm_mem
-            self.out_full = symm_mem.empty((self.per, self.ld_out), dtype=torch.float32, device=dev)
-            self.symm = symm_mem.rendezvous(self.out_full, group if group is not None else dist.group.WORLD)
+            if (reuse is not None and reuse.peer and reuse.symm is not None and reuse.world == world
+                    and reuse.rank == rank and reuse.dg.n == n):
+                self.out_full, self.symm = reuse.out_full, reuse.symm      # the result block does not depend on the support
+            else:
+                self.out_full = symm_mem.empty((self.per, self.ld_out), dtype=torch.float32, device=dev)
+                self.symm = symm_mem.rendezvous(self.out_full, group if group is not None else dist.group.WORLD)
             self.ptrs = torch.tensor([int(p) for p in self.symm.buffer_ptrs], dtype=torch.int64, device=dev)
         if self.peer:
             self.out = self.out_full[:max(self.n_rows, 1), :n]

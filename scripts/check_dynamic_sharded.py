@@ -27,6 +27,11 @@ def draw(g, k):
 batch1 = draw(g0, k_ins)                      # first update also pays one-time costs (lazy kernel loads, peer views)
 g1 = g0.copy(); g1.add_edges_from(batch1)
 batch2 = draw(g1, k_ins)                      # second update is the timed one
+if len(sys.argv) > 4 and sys.argv[4] == "newdeg":
+    # one more neighbour for the biggest hub: a NEW distinct degree, every signature changes length and the
+    # plan is rebuilt on the previous plan's symmetric-memory allocations (ShardedDegreeHSD(reuse=...))
+    hub = max(deg, key=deg.get)
+    batch2 = batch2 + [(min(hub, x), max(hub, x)) for x in low if not g1.has_edge(hub, x)][:1]
 g2 = g1.copy(); g2.add_edges_from(batch2)
 fresh = HSD(g2, "fresh", 0, hop, "wasserstein", signal="degree").structural_distance_device()
 for peer in (False, True):

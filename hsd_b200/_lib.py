@@ -17,7 +17,7 @@ HEADER_SYMBOLS = [
     "hsd_bfs_workspace_words", "hsd_bfs_set_workspace",
     "hsd_signature_transpose", "hsd_scatter_symmetric", "hsd_pairwise_l1", "hsd_pairwise_l1_sharded", "hsd_ring_signature_values",
     "hsd_pairwise_w1_merge", "hsd_pairwise_aligned", "hsd_pairwise_worker", "hsd_cheb_spmm", "hsd_laplacian_spmv", "hsd_ring_reduce", "hsd_characteristic_function", "hsd_topk_rows",
-    "hsd_fp32_peak_probe", "hsd_copy2d_to_host", "hsd_mirror_upper_to_lower_host", "hsd_exact_wavelets",
+    "hsd_fp32_peak_probe", "hsd_copy2d_to_host", "hsd_mirror_upper_to_lower_host", "hsd_exact_wavelets", "hsd_ring_dense_workspace_words", "hsd_ring_signature_degree_dense",
 ]
 
 
@@ -47,6 +47,9 @@ lib.hsd_ring_signature_degree.argtypes = [_P, _P, c_int32, _P, _P, c_int32, c_in
 lib.hsd_ring_signature_degree_allgather.argtypes = [_P, _P, c_int32, _P, _P, c_int32, c_int32, _P, _P, c_int32,
                                                     _P, c_int64, _P, c_int32, _P, c_int32, _P, c_int32, _P]
 lib.hsd_bfs_workspace_words.argtypes = [c_int32]
+lib.hsd_ring_dense_workspace_words.argtypes = [c_int32]
+lib.hsd_ring_signature_degree_dense.argtypes = [_P, _P, c_int32, _P, _P, c_int32, c_int32, _P, _P, c_int32,
+                                                _P, c_int64, _P, c_int32, _P, _P, c_int32, _P, _P, c_int64, c_int64, _P]
 lib.hsd_bfs_set_workspace.argtypes = [_P, c_int64]
 lib.hsd_bfs_rings.argtypes = [_P, _P, c_int32, _P, _P, c_int32, c_int32, _P, _P, _P]
 lib.hsd_signature_transpose.argtypes = [_P, c_int64, c_int32, c_int32, _P, c_int64, c_int32, _P, _P]
@@ -73,9 +76,10 @@ lib.hsd_exact_wavelets.argtypes = [_P, c_int64, _P, c_int32, c_double, c_double,
 lib.hsd_copy2d_to_host.argtypes = [_P, c_int64, _P, c_int64, c_int64, c_int64, _P]
 lib.hsd_mirror_upper_to_lower_host.argtypes = [_P, c_int64, c_int32, c_int32, c_int32, c_int32]
 for _name in HEADER_SYMBOLS:
-    if _name not in ("hsd_last_error_string", "hsd_bfs_workspace_words"):
+    if _name not in ("hsd_last_error_string", "hsd_bfs_workspace_words", "hsd_ring_dense_workspace_words"):
         getattr(lib, _name).restype = c_int32
 lib.hsd_bfs_workspace_words.restype = c_int64
+lib.hsd_ring_dense_workspace_words.restype = c_int64
 
 
 class HSDError(RuntimeError):

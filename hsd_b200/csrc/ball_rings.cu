@@ -1,0 +1,232 @@
+// K1/K2, dense variant — k-hop rings of MANY sources by bitmap dynamic programming.
+//
+// Reference loop replaced: tools/hierarchy.py:25-38 run for every node (tools/hierarchy.py:16-22) and,
+// for degree-valued ring signals, the sort + searchsorted inside scipy.stats.wasserstein_distance
+// (model/HSD.py:103-112) — the same outputs as bfs_rings.cu, bit for bit.
+//
+// The frontier-expansion kernel (bfs_rings.cu) walks every adjacency list incident to ball_{H-1}(s)
+// one 4-byte column index at a time: ~10 instructions and one random shared-memory bitmap lookup per
+// edge visit, level barriers, scans.  When (almost) ALL sources are wanted, the balls obey
+//     ball_h(s) = {s}  U  OR_{u in N(s)} ball_{h-1}(u),
+// so level h of every source is deg(s) coalesced ORs of N-bit rows of the previous level's table:
+// 2E row reads of N/8 bytes per level, streamed with 16-byte loads, no atomics, no barriers, and the
+// rows of the hubs (read deg times) stay in L2.  At C3 (100k nodes, 4 hops) that is 3 x 12.5 GB of
+// row reads instead of 1.5e10 edge visits.  ring_h = ball_h & ~ball_{h-1}; the degree CDF is the same
+// prefix popcount over the degree-ordered ids as in the frontier kernel.
+//
+// Cost is O(E N / 32) per level whatever the ball sizes, and the two tables take 2 N^2 / 8 bytes
+// (2.5 GB at N = 100k), so the host side picks this variant when most sources are requested and the
+// workspace fits; few sources or huge sparse graphs stay on the frontier kernel.
+#include <algorithm>
+#include "hsd_common.cuh"
+
+namespace hsd {
+
+// ball_1: T[s] = {s} U N(s).  One thread per CSR entry / per node; the table was zeroed before.
+__global__ void __launch_bounds__(256)
+ball1_scatter_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int n, int64_t nnz,
+                     int64_t row_words, uint32_t* __restrict__ T) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < n) atomicOr(T + idx * row_words + (idx >> 5), 1u << (idx & 31));
+    if (idx >= nnz) return;
+    int lo = 0, hi = n;                       // row of entry idx: largest s with rowptr[s] <= idx
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if ((int64_t)__ldg(rowptr + mid) <= idx) lo = mid; else hi = mid;
+    }
+    const int u = __ldg(col + idx);
+    atomicOr(T + (int64_t)lo * row_words + (u >> 5), 1u << (u & 31));
+}
+
+// T_next[s][chunk] = T_prev[s][chunk] | OR_{u in N(s)} T_prev[u][chunk]; a CTA owns 256 x 16 bytes of a row.
+// srcs == nullptr: all nodes, biggest degree first (ids are degree-ascending) so the hub rows, whose
+// CTAs read the most, start early.
+__global__ void __launch_bounds__(256, 4)
+ball_or_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int n,
+               const int32_t* __restrict__ srcs, int64_t row_words, const uint32_t* __restrict__ Tp,
+               uint32_t* __restrict__ Tn) {
+    const int s = srcs ? __ldg(srcs + blockIdx.x) : n - 1 - (int)blockIdx.x;
+    const int64_t w4 = ((int64_t)blockIdx.y * blockDim.x + threadIdx.x) * 4;    // first word of this thread's uint4
+    if (w4 >= row_words) return;
+    const uint32_t* base = Tp + w4;
+    uint4 acc = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)s * row_words));
+    const int e0 = __ldg(rowptr + s), e1 = __ldg(rowptr + s + 1);
+    int e = e0;
+    for (; e + 8 <= e1; e += 8) {
+        int u[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) u[q] = __ldg(col + e + q);
+        uint4 x[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) x[q] = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)u[q] * row_words));
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { acc.x |= x[q].x; acc.y |= x[q].y; acc.z |= x[q].z; acc.w |= x[q].w; }
+    }
+    for (; e < e1; ++e) {
+        const int u = __ldg(col + e);
+        const uint4 x = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)u * row_words));
+        acc.x |= x.x; acc.y |= x.y; acc.z |= x.z; acc.w |= x.w;
+    }
+    *reinterpret_cast<uint4*>(Tn + (int64_t)s * row_words + w4) = acc;
+}
+
+struct RingCdfArgs {
+    const int32_t* rowptr;
+    const int32_t* src_nodes;
+    const int32_t* out_rows;
+    int32_t n_words, hops, h;                     // h = hop of this launch (1..hops)
+    int64_t row_words;
+    const uint32_t* cur;                          // ball_h table
+    const uint32_t* prev;                         // ball_{h-1} table (h >= 2)
+    const int32_t* bin_end;
+    const float* delta;
+    int32_t n_bins;
+    float* sig;
+    int64_t sig_ld;
+    float* const* sig_peers;
+    int32_t n_peers;
+    int32_t* ring_sizes;
+    uint32_t* ring_bitmaps;
+    int32_t empty_as_zero;
+    int32_t* status;
+};
+
+// One CTA per source: ring_h = ball_h & ~ball_{h-1}, its size, its bitmap (optional) and its
+// delta-scaled degree CDF — the same arithmetic as the epilogue of bfs_ring_signature_kernel
+// (integer prefix popcount at the bin boundaries, one IEEE divide), so both variants agree bit for bit.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+ring_cdf_kernel(const RingCdfArgs p) {
+    extern __shared__ uint32_t rc_smem[];
+    __shared__ int warp_tot[THREADS / 32];
+    uint32_t* Fn = rc_smem;
+    uint32_t* P = rc_smem + p.n_words;
+    const int tid = threadIdx.x, nw = p.n_words, hops1 = p.hops + 1, nb1 = p.n_bins - 1, h = p.h;
+    const int s = p.src_nodes[blockIdx.x];
+    const int64_t row = p.out_rows[blockIdx.x];
+    if (h == 1) {       // hop 0 rides on the first launch: the ring is the source alone
+        if (tid == 0) {
+            if (p.ring_sizes) p.ring_sizes[row * hops1] = 1;
+            if (p.sig) {
+                const float d0 = (float)(p.rowptr[s + 1] - p.rowptr[s]);
+                p.sig[row * p.sig_ld] = d0;
+                for (int r = 0; r < p.n_peers; ++r) p.sig_peers[r][row * p.sig_ld] = d0;
+            }
+        }
+        if (p.ring_bitmaps) {
+            uint32_t* dst = p.ring_bitmaps + (row * hops1) * (int64_t)nw;
+            for (int w = tid; w < nw; w += THREADS) dst[w] = (w == (s >> 5)) ? (1u << (s & 31)) : 0u;
+        }
+    }
+    const uint32_t* cur = p.cur + (int64_t)s * p.row_words;
+    const uint32_t* prv = p.prev ? p.prev + (int64_t)s * p.row_words : nullptr;
+    const int cpt = (nw + THREADS - 1) / THREADS;
+    const int w_lo = min(tid * cpt, nw), w_hi = min(w_lo + cpt, nw);
+    int local = 0;
+    for (int w = w_lo; w < w_hi; ++w) {
+        const uint32_t before = prv ? prv[w] : ((w == (s >> 5)) ? (1u << (s & 31)) : 0u);
+        const uint32_t r = cur[w] & ~before;
+        Fn[w] = r;
+        local += __popc(r);
+    }
+    int n_ring;
+    int run = block_exclusive_scan<THREADS>(local, warp_tot, &n_ring);
+    for (int w = w_lo; w < w_hi; ++w) {
+        P[w] = (uint32_t)run;
+        run += __popc(Fn[w]);
+    }
+    __syncthreads();
+    if (tid == 0 && p.ring_sizes) p.ring_sizes[row * hops1 + h] = n_ring;
+    if (p.ring_bitmaps) {
+        uint32_t* dst = p.ring_bitmaps + (row * hops1 + h) * (int64_t)nw;
+        for (int w = tid; w < nw; w += THREADS) dst[w] = Fn[w];
+    }
+    if (p.sig) {
+        const int64_t dst_off = row * p.sig_ld + 1 + (int64_t)(h - 1) * nb1;
+        float* dst = p.sig + dst_off;
+        if (n_ring > 0) {
+            const float n_f = (float)n_ring;
+            for (int b = tid; b < nb1; b += THREADS) {
+                const int e = __ldg(p.bin_end + b);  // < n_nodes for b < n_bins-1
+                const int cnt = (int)P[e >> 5] + __popc(Fn[e >> 5] & ((1u << (e & 31)) - 1u));
+                const float val = __fdiv_rn((float)cnt * __ldg(p.delta + b), n_f);
+                dst[b] = val;
+                for (int r = 0; r < p.n_peers; ++r) p.sig_peers[r][dst_off + b] = val;
+            }
+        } else {
+            if (!p.empty_as_zero && tid == 0) atomicOr(p.status, 1);
+            for (int b = tid; b < nb1; b += THREADS) {
+                const float val = p.empty_as_zero ? __ldg(p.delta + b) : 0.f;
+                dst[b] = val;
+                for (int r = 0; r < p.n_peers; ++r) p.sig_peers[r][dst_off + b] = val;
+            }
+        }
+    }
+}
+
+static inline int64_t dense_row_words(int32_t n_nodes) { return ((int64_t)(n_nodes + 31) / 32 + 3) / 4 * 4; }
+
+}  // namespace hsd
+
+extern "C" int64_t hsd_ring_dense_workspace_words(int32_t n_nodes) {
+    return 2 * (int64_t)n_nodes * hsd::dense_row_words(n_nodes);
+}
+
+extern "C" int hsd_ring_signature_degree_dense(const int32_t* rowptr, const int32_t* col, int32_t n_nodes,
+                                               const int32_t* src_nodes, const int32_t* out_rows, int32_t n_src,
+                                               int32_t hops, const int32_t* bin_end, const float* delta,
+                                               int32_t n_bins, float* sig, int64_t sig_ld,
+                                               float* const* sig_peers, int32_t n_peers, int32_t* ring_sizes,
+                                               uint32_t* ring_bitmaps, int32_t empty_as_zero, int32_t* status,
+                                               uint32_t* workspace, int64_t workspace_words, int64_t nnz,
+                                               void* stream_) {
+    using namespace hsd;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    HSD_REQUIRE(rowptr && col && src_nodes && out_rows && workspace, "null pointer");
+    HSD_REQUIRE(n_nodes > 0 && n_src >= 0 && hops >= 0 && nnz >= 0, "bad sizes");
+    HSD_REQUIRE(n_peers >= 0 && n_peers <= 64 && (n_peers == 0 || (sig && sig_peers)), "bad peer list");
+    if (sig) {
+        HSD_REQUIRE(bin_end && delta && n_bins >= 1 && status, "sig requested without support tables");
+        HSD_REQUIRE(sig_ld >= 1 + (int64_t)hops * (n_bins - 1), "sig_ld too small");
+    }
+    const int64_t rw = dense_row_words(n_nodes);
+    HSD_REQUIRE(workspace_words >= 2 * (int64_t)n_nodes * rw, "workspace smaller than hsd_ring_dense_workspace_words");
+    HSD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "workspace must be 16-byte aligned");
+    if (n_src == 0) return HSD_OK;
+    const int nw = (n_nodes + 31) / 32;
+    const size_t smem = (size_t)2 * nw * sizeof(uint32_t);
+    HSD_REQUIRE(smem <= 200 * 1024, "graph too large for the dense variant's shared-memory CDF pass");
+    uint32_t* T[2] = {workspace, workspace + (int64_t)n_nodes * rw};
+    RingCdfArgs a;
+    a.rowptr = rowptr; a.src_nodes = src_nodes; a.out_rows = out_rows; a.n_words = nw; a.hops = hops;
+    a.row_words = rw; a.bin_end = bin_end; a.delta = delta; a.n_bins = sig ? n_bins : 1; a.sig = sig; a.sig_ld = sig_ld;
+    a.sig_peers = sig_peers; a.n_peers = n_peers; a.ring_sizes = ring_sizes; a.ring_bitmaps = ring_bitmaps;
+    a.empty_as_zero = empty_as_zero; a.status = status;
+    HSD_CUDA_TRY(cudaFuncSetAttribute(ring_cdf_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HSD_REQUIRE(hops >= 1, "the dense variant needs hops >= 1 (hop 0 alone: use hsd_ring_signature_degree)");
+    // ---- ball_1 ----
+    HSD_CUDA_TRY(cudaMemsetAsync(T[0], 0, (size_t)n_nodes * rw * sizeof(uint32_t), stream));
+    {
+        const int64_t items = std::max<int64_t>(nnz, n_nodes);
+        ball1_scatter_kernel<<<(unsigned)((items + 255) / 256), 256, 0, stream>>>(rowptr, col, n_nodes, nnz, rw, T[0]);
+        HSD_CUDA_TRY(cudaGetLastError());
+    }
+    a.h = 1; a.cur = T[0]; a.prev = nullptr;
+    ring_cdf_kernel<256><<<n_src, 256, smem, stream>>>(a);
+    HSD_CUDA_TRY(cudaGetLastError());
+    const unsigned chunks = (unsigned)((rw / 4 + 255) / 256);
+    for (int h = 2; h <= hops; ++h) {
+        const uint32_t* Tp = T[h & 1];        // h = 2 reads T[0]
+        uint32_t* Tn = T[(h + 1) & 1];
+        if (h < hops) {
+            ball_or_kernel<<<dim3(n_nodes, chunks), 256, 0, stream>>>(rowptr, col, n_nodes, nullptr, rw, Tp, Tn);
+        } else {
+            ball_or_kernel<<<dim3(n_src, chunks), 256, 0, stream>>>(rowptr, col, n_nodes, src_nodes, rw, Tp, Tn);
+        }
+        HSD_CUDA_TRY(cudaGetLastError());
+        a.h = h; a.cur = Tn; a.prev = Tp;
+        ring_cdf_kernel<256><<<n_src, 256, smem, stream>>>(a);
+        HSD_CUDA_TRY(cudaGetLastError());
+    }
+    return HSD_OK;
+}

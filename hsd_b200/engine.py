@@ -118,6 +118,13 @@ class DeviceGraph:
     def n_words(self) -> int:
         return (self.n + 31) // 32
 
+    @property
+    def nnz(self) -> int:
+        """CSR entries (rowptr[n]); the col array is padded beyond it for 16-byte reads."""
+        if getattr(self, "_nnz", None) is None:
+            self._nnz = int(self.rowptr[-1].item())
+        return self._nnz
+
     def k_used(self, hops: int) -> int:
         """Signature length: hop 0 is one scalar (the source degree), every later hop
         is the delta-scaled CDF over the B-1 gaps of the shared support."""
@@ -143,6 +150,73 @@ def ensure_bfs_workspace(n_nodes: int, device) -> None:
         ws = torch.empty(words, dtype=torch.int32, device=dev)
         _BFS_WS[key] = ws
     check(lib.hsd_bfs_set_workspace(_ptr(ws), ws.numel()))
+
+
+_DENSE_WS = {}   # device index -> int32 workspace tensor (grow-only) of the dense ring variant
+
+
+def ring_algorithm(n_nodes: int, n_src: int, hops: int, device) -> str:
+    """'dense' (hsd_ring_signature_degree_dense: bitmap dynamic programming over all nodes) or 'frontier'
+    (hsd_ring_signature_degree: one frontier-expansion BFS per source).  Dense pays O(E N / 32) per level
+    for ALL nodes at the intermediate levels, so it is chosen when at least an eighth of the nodes are
+    sources (a rank of an 8-GPU job; HSD_RING_DENSE_MIN_FRAC), hops >= 2 and its two N x N-bit tables fit
+    in a quarter of the free device memory.  HSD_RING_ALGO=dense|frontier overrides
+    (dense still needs hops >= 1)."""
+    import os
+    force = os.environ.get("HSD_RING_ALGO", "")
+    if hops < 1 or (n_nodes + 31) // 32 * 8 > 200 * 1024:
+        return "frontier"
+    if force in ("dense", "frontier"):
+        return force
+    min_frac = float(os.environ.get("HSD_RING_DENSE_MIN_FRAC", "0.125"))
+    if hops < 2 or n_src < min_frac * n_nodes or n_nodes < 512:
+        return "frontier"
+    words = int(lib.hsd_ring_dense_workspace_words(n_nodes))
+    dev = torch.device(device)
+    ws = _DENSE_WS.get(dev.index if dev.index is not None else torch.cuda.current_device())
+    if ws is not None and ws.numel() >= words:
+        return "dense"
+    free, _ = torch.cuda.mem_get_info(dev)
+    return "dense" if words * 4 <= free // 4 else "frontier"
+
+
+def dense_ring_workspace(n_nodes: int, device) -> torch.Tensor:
+    words = int(lib.hsd_ring_dense_workspace_words(n_nodes))
+    dev = torch.device(device)
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    ws = _DENSE_WS.get(key)
+    if ws is None or ws.numel() < words:
+        _DENSE_WS[key] = None
+        ws = torch.empty(words, dtype=torch.int32, device=dev)
+        _DENSE_WS[key] = ws
+    return ws
+
+
+def launch_ring_signature(dg_rowptr, dg_col, n, nnz, src, out_rows, n_src, hops, bin_end, delta, n_bins,
+                          sig, ld, sizes, bitmaps, empty_as_zero, status, device, peers=None, threads=0,
+                          stream=None) -> str:
+    """One call site for the K1/K2 entry points: picks the dense or the frontier variant (same outputs,
+    bit for bit) and launches it on `stream` (default: the current stream).  Returns the variant used."""
+    stream = _stream() if stream is None else stream
+    algo = ring_algorithm(n, n_src, hops, device)
+    n_peers = int(peers.numel()) if peers is not None else 0
+    if algo == "dense":
+        ws = dense_ring_workspace(n, device)
+        check(lib.hsd_ring_signature_degree_dense(
+            _ptr(dg_rowptr), _ptr(dg_col), n, _ptr(src), _ptr(out_rows), n_src, hops, _ptr(bin_end), _ptr(delta),
+            n_bins, _ptr(sig), ld, _ptr(peers) if n_peers else None, n_peers, _ptr(sizes), _ptr(bitmaps),
+            empty_as_zero, _ptr(status), _ptr(ws), ws.numel(), nnz, stream))
+        return algo
+    ensure_bfs_workspace(n, device)
+    if n_peers:
+        check(lib.hsd_ring_signature_degree_allgather(
+            _ptr(dg_rowptr), _ptr(dg_col), n, _ptr(src), _ptr(out_rows), n_src, hops, _ptr(bin_end), _ptr(delta),
+            n_bins, _ptr(sig), ld, _ptr(peers), n_peers, _ptr(sizes), empty_as_zero, _ptr(status), threads, stream))
+    else:
+        check(lib.hsd_ring_signature_degree(
+            _ptr(dg_rowptr), _ptr(dg_col), n, _ptr(src), _ptr(out_rows), n_src, hops, _ptr(bin_end), _ptr(delta),
+            n_bins, _ptr(sig), ld, _ptr(sizes), _ptr(bitmaps), empty_as_zero, _ptr(status), threads, stream))
+    return algo
 
 
 def ring_signature_degree(dg: DeviceGraph, hops: int, rows: Optional[torch.Tensor] = None,
@@ -178,12 +252,8 @@ def ring_signature_degree(dg: DeviceGraph, hops: int, rows: Optional[torch.Tenso
     bitmaps = (torch.empty((n_src, hops + 1, dg.n_words), dtype=torch.int32, device=dev)
                if want_bitmaps else None)
     status = torch.zeros(1, dtype=torch.int32, device=dev)
-    ensure_bfs_workspace(dg.n, dev)
-    check(lib.hsd_ring_signature_degree(
-        _ptr(dg.rowptr), _ptr(dg.col), dg.n, _ptr(src), _ptr(out_rows), n_src, hops,
-        _ptr(dg.bin_end), _ptr(dg.delta), dg.n_bins,
-        _ptr(sig), ld, _ptr(sizes), _ptr(bitmaps), 1 if empty == "zero" else 0,
-        _ptr(status), 0, _stream()))
+    launch_ring_signature(dg.rowptr, dg.col, dg.n, dg.nnz, src, out_rows, n_src, hops, dg.bin_end, dg.delta,
+                          dg.n_bins, sig, ld, sizes, bitmaps, 1 if empty == "zero" else 0, status, dev)
     return sig, sizes, bitmaps, status
 
 
@@ -335,6 +405,7 @@ class HostDegreePipeline:
         if delta.size == 0:
             delta = np.zeros(1, dtype=np.float32)
         self.n = g.n
+        self.nnz = g.nnz
         self.n_bins = int(sup.size)
         self.host = {k: _pin(v) for k, v in dict(rowptr=o.rowptr, col=o.col if o.col.size else np.zeros(1, np.int32),
                                                  orig_of=o.orig_of, new_of=o.new_of, bin_end=bin_end,
@@ -394,12 +465,9 @@ class HostDegreePipeline:
         arrived = []
         if out.stride(1) != 1:
             raise ValueError("out must be row-major")
-        ensure_bfs_workspace(self.n, self.dev)
-        check(lib.hsd_ring_signature_degree(
-            _ptr(d["rowptr"]), _ptr(d["col"]), self.n, _ptr(d["new_of"]), _ptr(self.out_rows_idx), self.n,
-            self.hops, _ptr(d["bin_end"]), _ptr(d["delta"]), self.n_bins,
-            _ptr(self.sig), self.sig.stride(0), None, None, 1 if self.empty == "zero" else 0,
-            _ptr(self.status), 0, _stream()))
+        launch_ring_signature(d["rowptr"], d["col"], self.n, self.nnz, d["new_of"], self.out_rows_idx, self.n,
+                              self.hops, d["bin_end"], d["delta"], self.n_bins, self.sig, self.sig.stride(0),
+                              None, None, 1 if self.empty == "zero" else 0, self.status, self.dev)
         signature_transpose(self.sig, self.k_used, self.sigT, 0)
         for (p0, pr) in self.panels:
             if self.full:

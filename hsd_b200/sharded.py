@@ -211,6 +211,14 @@ class ShardedDegreeHSD:
                     engine._ptr(self.sig_all), self.ld, engine._ptr(self.sizes), None,
                     1 if self.empty == "zero" else 0, engine._ptr(self.status), threads, stream))
 
+        if engine.ring_algorithm(dg.n, self.n_src, self.hops, dg.rowptr.device) == "dense":
+            # (world <= 2) most nodes are this rank's sources: bitmap dynamic programming over all nodes,
+            # signature rows stored into the peers' tables by its CDF pass like the frontier kernel does
+            engine.launch_ring_signature(dg.rowptr, dg.col, dg.n, dg.nnz, self.src, self.out_rows, self.n_src,
+                                         self.hops, dg.bin_end, dg.delta, dg.n_bins, self.sig_all, self.ld,
+                                         self.sizes, None, 1 if self.empty == "zero" else 0, self.status,
+                                         dg.rowptr.device, peers=self.sig_peer_ptrs)
+            return
         if self.hub_split is None:
             launch(self.src, self.out_rows, 0, engine._stream())
             return

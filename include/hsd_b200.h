@@ -95,6 +95,24 @@ int hsd_ring_signature_degree_allgather(const int32_t* rowptr, const int32_t* co
                                         int32_t* ring_sizes, int32_t empty_as_zero, int32_t* status,
                                         int32_t cta_threads, void* stream);
 
+/* Dense variant of the two entry points above, for when (almost) every node is a source: the balls obey
+ * ball_h(s) = {s} U OR_{u in N(s)} ball_{h-1}(u), so a level of ALL nodes is 2E coalesced ORs of N-bit rows
+ * of the previous level's table (no per-edge bitmap lookups, no atomics after level 1, no level barriers);
+ * ring_h = ball_h & ~ball_{h-1}, then the same prefix-popcount CDF.  Outputs are bit-identical to
+ * hsd_ring_signature_degree (sig / ring_sizes / ring_bitmaps / status, sig_peers as in the _allgather entry,
+ * nullable).  Intermediate levels are computed for all n_nodes nodes whatever n_src is, and the cost is
+ * O(E N / 32) per level whatever the ball sizes: the host picks this variant when most nodes are sources
+ * and the workspace fits.  workspace: hsd_ring_dense_workspace_words(n_nodes) uint32 words (two N x N-bit
+ * tables), 16-byte aligned, caller-owned; nnz = rowptr[n_nodes]; hops >= 1. */
+int64_t hsd_ring_dense_workspace_words(int32_t n_nodes);
+int hsd_ring_signature_degree_dense(const int32_t* rowptr, const int32_t* col, int32_t n_nodes,
+                                    const int32_t* src_nodes, const int32_t* out_rows, int32_t n_src,
+                                    int32_t hops, const int32_t* bin_end, const float* delta, int32_t n_bins,
+                                    float* sig, int64_t sig_ld, float* const* sig_peers, int32_t n_peers,
+                                    int32_t* ring_sizes, uint32_t* ring_bitmaps, int32_t empty_as_zero,
+                                    int32_t* status, uint32_t* workspace, int64_t workspace_words, int64_t nnz,
+                                    void* stream);
+
 /* Graphs above ~400k nodes: the four N-bit bitmaps of a source no longer fit shared memory.  The
  * BFS entry points then use a caller-owned DEVICE workspace of hsd_bfs_workspace_words(n_nodes)
  * uint32 words (0 = not needed), registered per host thread with hsd_bfs_set_workspace (NULL

@@ -116,3 +116,35 @@ def test_empty_ring_policy():
     D, sizes = engine.degree_distance_device(dgz, 2, empty="zero")
     ref = O.degree_distance_rows(_oracle_adj(g), 2, list(range(6)), empty="zero")
     np.testing.assert_allclose(D.cpu().numpy(), ref, rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("n,m,hops", [(700, 3, 1), (700, 3, 2), (3000, 5, 3), (5000, 2, 4)])
+def test_dense_and_frontier_ring_variants_agree_bitwise(n, m, hops, monkeypatch):
+    """hsd_ring_signature_degree_dense (bitmap dynamic programming over all nodes) against
+    hsd_ring_signature_degree (frontier BFS per source): signatures, ring sizes, ring bitmaps and the
+    empty-ring flag must be identical — also with isolated nodes, a self-loop and a source subset."""
+    import torch
+    from hsd_b200 import engine
+    from hsd_b200.graph import CSRGraph, powerlaw_graph
+    g0 = powerlaw_graph(n, m, seed=n)
+    rows = np.repeat(np.arange(g0.n), np.diff(g0.rowptr))
+    e = np.stack([rows, g0.col], 1)
+    e = np.concatenate([e[rows < g0.col], [[5, 5]]])               # one self-loop
+    g = CSRGraph.from_edges(n + 3, e)                              # three isolated nodes (empty rings)
+    dg = engine.DeviceGraph.upload(g, include_zero=True)
+    subset = torch.arange(0, g.n, 2, dtype=torch.int32, device="cuda")   # >= half the nodes
+    out = {}
+    for algo in ("frontier", "dense"):
+        monkeypatch.setenv("HSD_RING_ALGO", algo)
+        assert engine.ring_algorithm(g.n, g.n, hops, "cuda") == algo
+        full = engine.ring_signature_degree(dg, hops, want_bitmaps=True, empty="zero")
+        raising = engine.ring_signature_degree(dg, hops, empty="raise", want_sizes=False)
+        part = engine.ring_signature_degree(dg, hops, rows=subset, want_bitmaps=True, empty="zero")
+        torch.cuda.synchronize()
+        out[algo] = (full, raising, part)
+    for a, b in zip(out["frontier"], out["dense"]):
+        for x, y in zip(a, b):
+            assert (x is None) == (y is None)
+            if x is not None:
+                assert torch.equal(x, y)
+    assert int(out["dense"][1][3].item()) & 1                      # isolated nodes raise the empty-ring flag

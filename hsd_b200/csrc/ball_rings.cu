@@ -97,10 +97,10 @@ struct RingCdfArgs {
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
 ring_cdf_kernel(const RingCdfArgs p) {
-    extern __shared__ uint32_t rc_smem[];
+    extern __shared__ __align__(16) uint32_t rc_smem[];
     __shared__ int warp_tot[THREADS / 32];
-    uint32_t* Fn = rc_smem;
-    uint32_t* P = rc_smem + p.n_words;
+    uint32_t* Fn = rc_smem;                       // row_words words (16-byte granules)
+    uint32_t* P = rc_smem + p.row_words;          // n_words words
     const int tid = threadIdx.x, nw = p.n_words, hops1 = p.hops + 1, nb1 = p.n_bins - 1, h = p.h;
     const int s = p.src_nodes[blockIdx.x];
     const int64_t row = p.out_rows[blockIdx.x];
@@ -118,17 +118,26 @@ ring_cdf_kernel(const RingCdfArgs p) {
             for (int w = tid; w < nw; w += THREADS) dst[w] = (w == (s >> 5)) ? (1u << (s & 31)) : 0u;
         }
     }
-    const uint32_t* cur = p.cur + (int64_t)s * p.row_words;
-    const uint32_t* prv = p.prev ? p.prev + (int64_t)s * p.row_words : nullptr;
+    // ring words into shared memory with coalesced 16-byte loads (rows are 16-byte aligned and padded
+    // with zero bits), then every thread popcounts a contiguous run of words for the block scan
+    const uint4* cur4 = reinterpret_cast<const uint4*>(p.cur + (int64_t)s * p.row_words);
+    const uint4* prv4 = p.prev ? reinterpret_cast<const uint4*>(p.prev + (int64_t)s * p.row_words) : nullptr;
+    const int n4 = (int)(p.row_words / 4);
+    for (int q = tid; q < n4; q += THREADS) {
+        uint4 c = __ldg(cur4 + q);
+        if (prv4) {
+            const uint4 b = __ldg(prv4 + q);
+            c.x &= ~b.x; c.y &= ~b.y; c.z &= ~b.z; c.w &= ~b.w;
+        }
+        *reinterpret_cast<uint4*>(Fn + 4 * q) = c;
+    }
+    __syncthreads();
+    if (!prv4 && tid == 0) Fn[s >> 5] &= ~(1u << (s & 31));     // hop 1: ball_1 minus the source itself
+    __syncthreads();
     const int cpt = (nw + THREADS - 1) / THREADS;
     const int w_lo = min(tid * cpt, nw), w_hi = min(w_lo + cpt, nw);
     int local = 0;
-    for (int w = w_lo; w < w_hi; ++w) {
-        const uint32_t before = prv ? prv[w] : ((w == (s >> 5)) ? (1u << (s & 31)) : 0u);
-        const uint32_t r = cur[w] & ~before;
-        Fn[w] = r;
-        local += __popc(r);
-    }
+    for (int w = w_lo; w < w_hi; ++w) local += __popc(Fn[w]);
     int n_ring;
     int run = block_exclusive_scan<THREADS>(local, warp_tot, &n_ring);
     for (int w = w_lo; w < w_hi; ++w) {
@@ -194,7 +203,7 @@ extern "C" int hsd_ring_signature_degree_dense(const int32_t* rowptr, const int3
     HSD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "workspace must be 16-byte aligned");
     if (n_src == 0) return HSD_OK;
     const int nw = (n_nodes + 31) / 32;
-    const size_t smem = (size_t)2 * nw * sizeof(uint32_t);
+    const size_t smem = (size_t)(rw + nw) * sizeof(uint32_t);
     HSD_REQUIRE(smem <= 200 * 1024, "graph too large for the dense variant's shared-memory CDF pass");
     uint32_t* T[2] = {workspace, workspace + (int64_t)n_nodes * rw};
     RingCdfArgs a;

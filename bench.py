@@ -4,7 +4,7 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--workload c2|c3|NODESxHOPS]
 
 One "step" = one full pass of the hot path over the workload graph: k-hop rings
-(BFS kernel) -> per-ring degree CDF signatures -> (N>1: one NCCL all-gather of
+(bitmap dynamic programming over all nodes, or one frontier BFS per source) -> per-ring degree CDF signatures -> (N>1: one NCCL all-gather of
 the signature table, or peer-memory stores fused into the BFS kernel) -> pairwise W1 (L1
 between signatures) for this rank's share of the symmetric tiles.
 `value` is whole-job unordered node pairs / second with the graph already in HBM;
@@ -378,28 +378,46 @@ def measure_degree_path(ctx, g, hops, steps, warmup, workload_key):
         "flops_per_launch": flops, "ms_per_launch": pair_ms,
         "note": "tensor cores not applicable (|a-b| is not a contraction); FMA-counted peak would be 2x this",
     }
-    # ---- secondary: BFS + signature kernel against HBM/L2 ----
-    own = slice(plan.rank * plan.per, plan.rank * plan.per + plan.n_src)   # this rank's BFS sources in the table
-    sig_rows = plan.sig_all[own, 1:k_alg].double()
-    nb1 = dg.n_bins - 1
-    sizes = plan.sizes[own].double()
-    sup_max = float(dg.support[-1])
-    edges_scanned = float((plan.sig_all[own, 0].double()).sum().item())  # hop 0 expands the source
-    for h in range(1, hops):   # rings 1..H-1 are expanded; sum of member degrees = n * mean = n * (max - sum_b CDF*delta)
-        mean_deg = sup_max - sig_rows[:, (h - 1) * nb1:h * nb1].sum(1)
-        edges_scanned += float((sizes[:, h] * mean_deg).sum().item())
-    bfs_bytes = 4.0 * edges_scanned + 4.0 * k_alg * plan.n_src
+    # ---- secondary: ring + signature phase against HBM/L2 ----
+    own = slice(plan.rank * plan.per, plan.rank * plan.per + plan.n_src)   # this rank's sources in the table
+    variant = engine.ring_algorithm(n, plan.n_src, hops, dev)
+    if variant == "dense":
+        # bitmap dynamic programming: level h >= 2 reads (entries + rows) N-bit rows of the previous table and
+        # writes one row per computed node; intermediate levels cover all nodes, the last one this rank's sources
+        row_b = ((n + 31) // 32 + 3) // 4 * 4 * 4.0
+        nnz = float(dg.nnz)
+        ring_bytes = n * row_b + plan.n_src * row_b                      # level 1: table build + CDF read
+        for h in range(2, hops + 1):
+            rows_h = n if h < hops else plan.n_src
+            ring_bytes += (nnz * rows_h / n + rows_h) * row_b + rows_h * row_b
+        ring_bytes += 4.0 * k_alg * plan.n_src
+        ring_kernel = "ball_or_cdf_kernel + ring_cdf_kernel (dense ring variant)"
+        ring_note = ("bitmap dynamic programming over all nodes: (H-1) levels of (2E+N) row reads of N/8 bytes; hub rows "
+                     "are re-read from L2, so DRAM traffic is below the algorithmic bytes")
+        edges_scanned = None
+    else:
+        sig_rows = plan.sig_all[own, 1:k_alg].double()
+        nb1 = dg.n_bins - 1
+        sizes = plan.sizes[own].double()
+        sup_max = float(dg.support[-1])
+        edges_scanned = float((plan.sig_all[own, 0].double()).sum().item())  # hop 0 expands the source
+        for h in range(1, hops):   # rings 1..H-1 are expanded; sum of member degrees = n * mean = n * (max - sum_b CDF*delta)
+            mean_deg = sup_max - sig_rows[:, (h - 1) * nb1:h * nb1].sum(1)
+            edges_scanned += float((sizes[:, h] * mean_deg).sum().item())
+        ring_bytes = 4.0 * edges_scanned + 4.0 * k_alg * plan.n_src
+        ring_kernel = "bfs_ring_signature_kernel (frontier ring variant)"
+        ring_note = "CSR and bitmaps are L2/SMEM resident, so the HBM fraction is structurally small (SURVEY H4)"
     roofline_bfs = {
-        "kernel": "bfs_ring_signature_kernel", "bound": "hbm", "achieved": bfs_bytes / (bfs_ms * 1e-3) / 1e9,
-        "peak": ctx.hbm_peak, "unit": "GB/s", "frac": bfs_bytes / (bfs_ms * 1e-3) / 1e9 / ctx.hbm_peak, "traffic": None,
+        "kernel": ring_kernel, "bound": "hbm", "achieved": ring_bytes / (bfs_ms * 1e-3) / 1e9,
+        "peak": ctx.hbm_peak, "unit": "GB/s", "frac": ring_bytes / (bfs_ms * 1e-3) / 1e9 / ctx.hbm_peak, "traffic": None,
         "peak_source": ctx.hbm_src,
-        "bytes_per_launch": bfs_bytes, "ms_per_launch": bfs_ms, "edges_scanned_per_launch": edges_scanned,
-        "note": "CSR and bitmaps are L2/SMEM resident, so the HBM fraction is structurally small (SURVEY H4)",
+        "bytes_per_launch": ring_bytes, "ms_per_launch": bfs_ms, "edges_scanned_per_launch": edges_scanned,
+        "note": ring_note,
     }
     rec = {"ms_per_step": ms_per_step, "value": value, "pairs": pairs, "peer": peer, "k_alg": k_alg,
            "n_bins": dg.n_bins, "stage_ms": {"bfs_signature": bfs_ms, "allgather_transpose": gather_ms, "pairwise": pair_ms},
            "roofline": roofline, "roofline_bfs": roofline_bfs, "clocks": clocks,
-           "launches_per_step": 3 if plan.n_rows else 2}
+           "launches_per_step": (3 if plan.n_rows else 2) + (2 * hops if variant == "dense" else 0)}
     return rec, plan, dg
 
 

@@ -91,20 +91,15 @@ struct RingCdfArgs {
     int32_t* status;
 };
 
-// One CTA per source: ring_h = ball_h & ~ball_{h-1}, its size, its bitmap (optional) and its
-// delta-scaled degree CDF — the same arithmetic as the epilogue of bfs_ring_signature_kernel
-// (integer prefix popcount at the bin boundaries, one IEEE divide), so both variants agree bit for bit.
+// Outputs of one (source, hop): ring size, ring bitmap (optional) and the delta-scaled degree CDF of
+// the ring whose words sit in shared memory (Fn) — the same arithmetic as the epilogue of
+// bfs_ring_signature_kernel (integer prefix popcount at the bin boundaries, one IEEE divide), so both
+// variants agree bit for bit.  Hop 0 rides on the hop-1 call.
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS)
-ring_cdf_kernel(const RingCdfArgs p) {
-    extern __shared__ __align__(16) uint32_t rc_smem[];
-    __shared__ int warp_tot[THREADS / 32];
-    uint32_t* Fn = rc_smem;                       // row_words words (16-byte granules)
-    uint32_t* P = rc_smem + p.row_words;          // n_words words
-    const int tid = threadIdx.x, nw = p.n_words, hops1 = p.hops + 1, nb1 = p.n_bins - 1, h = p.h;
-    const int s = p.src_nodes[blockIdx.x];
-    const int64_t row = p.out_rows[blockIdx.x];
-    if (h == 1) {       // hop 0 rides on the first launch: the ring is the source alone
+__device__ __forceinline__ void ring_outputs(const RingCdfArgs& p, const int s, const int64_t row, const int h,
+                                             uint32_t* __restrict__ Fn, uint32_t* __restrict__ P, int* warp_tot) {
+    const int tid = threadIdx.x, nw = p.n_words, hops1 = p.hops + 1, nb1 = p.n_bins - 1;
+    if (h == 1) {
         if (tid == 0) {
             if (p.ring_sizes) p.ring_sizes[row * hops1] = 1;
             if (p.sig) {
@@ -118,22 +113,6 @@ ring_cdf_kernel(const RingCdfArgs p) {
             for (int w = tid; w < nw; w += THREADS) dst[w] = (w == (s >> 5)) ? (1u << (s & 31)) : 0u;
         }
     }
-    // ring words into shared memory with coalesced 16-byte loads (rows are 16-byte aligned and padded
-    // with zero bits), then every thread popcounts a contiguous run of words for the block scan
-    const uint4* cur4 = reinterpret_cast<const uint4*>(p.cur + (int64_t)s * p.row_words);
-    const uint4* prv4 = p.prev ? reinterpret_cast<const uint4*>(p.prev + (int64_t)s * p.row_words) : nullptr;
-    const int n4 = (int)(p.row_words / 4);
-    for (int q = tid; q < n4; q += THREADS) {
-        uint4 c = __ldg(cur4 + q);
-        if (prv4) {
-            const uint4 b = __ldg(prv4 + q);
-            c.x &= ~b.x; c.y &= ~b.y; c.z &= ~b.z; c.w &= ~b.w;
-        }
-        *reinterpret_cast<uint4*>(Fn + 4 * q) = c;
-    }
-    __syncthreads();
-    if (!prv4 && tid == 0) Fn[s >> 5] &= ~(1u << (s & 31));     // hop 1: ball_1 minus the source itself
-    __syncthreads();
     const int cpt = (nw + THREADS - 1) / THREADS;
     const int w_lo = min(tid * cpt, nw), w_hi = min(w_lo + cpt, nw);
     int local = 0;
@@ -173,12 +152,129 @@ ring_cdf_kernel(const RingCdfArgs p) {
     }
 }
 
+// One CTA per source: ring_h = ball_h & ~ball_{h-1} from the two tables (hop 1, and rows too long for the
+// fused kernel below).
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+ring_cdf_kernel(const RingCdfArgs p) {
+    extern __shared__ __align__(16) uint32_t rc_smem[];
+    __shared__ int warp_tot[THREADS / 32];
+    uint32_t* Fn = rc_smem;                       // row_words words (16-byte granules)
+    uint32_t* P = rc_smem + p.row_words;          // n_words words
+    const int tid = threadIdx.x;
+    const int s = p.src_nodes[blockIdx.x];
+    const int64_t row = p.out_rows[blockIdx.x];
+    // ring words into shared memory with coalesced 16-byte loads (rows are 16-byte aligned and padded
+    // with zero bits)
+    const uint4* cur4 = reinterpret_cast<const uint4*>(p.cur + (int64_t)s * p.row_words);
+    const uint4* prv4 = p.prev ? reinterpret_cast<const uint4*>(p.prev + (int64_t)s * p.row_words) : nullptr;
+    const int n4 = (int)(p.row_words / 4);
+    for (int q = tid; q < n4; q += THREADS) {
+        uint4 c = __ldg(cur4 + q);
+        if (prv4) {
+            const uint4 b = __ldg(prv4 + q);
+            c.x &= ~b.x; c.y &= ~b.y; c.z &= ~b.z; c.w &= ~b.w;
+        }
+        *reinterpret_cast<uint4*>(Fn + 4 * q) = c;
+    }
+    __syncthreads();
+    if (!prv4 && tid == 0) Fn[s >> 5] &= ~(1u << (s & 31));     // hop 1: ball_1 minus the source itself
+    __syncthreads();
+    ring_outputs<THREADS>(p, s, row, p.h, Fn, P, warp_tot);
+}
+
+// Levels h >= 2 for rows of at most CHUNKS x 1024 words, FUSED: one CTA owns the whole row of node s,
+// ORs the neighbours' previous-level rows into registers (CHUNKS uint4 per thread), writes ball_h(s) and —
+// the new and the old row being in registers already — emits ring_h = new & ~old and its CDF in place,
+// instead of a second pass that re-reads both rows from the tables.  row_of_node (all-nodes launches):
+// output row of node s, -1 if s is not a requested source.
+template <int CHUNKS>
+__global__ void __launch_bounds__(256, CHUNKS >= 4 ? 3 : 4)
+ball_or_cdf_kernel(const int32_t* __restrict__ col, int n, const int32_t* __restrict__ srcs,
+                   const int32_t* __restrict__ row_of_node, const uint32_t* __restrict__ Tp,
+                   uint32_t* __restrict__ Tn, const RingCdfArgs p) {
+    extern __shared__ __align__(16) uint32_t rc_smem[];
+    __shared__ int warp_tot[256 / 32];
+    const int tid = threadIdx.x;
+    const int s = srcs ? __ldg(srcs + blockIdx.x) : n - 1 - (int)blockIdx.x;
+    const int64_t rw = p.row_words;
+    const int n4 = (int)(rw / 4);
+    uint4 old[CHUNKS], acc[CHUNKS];
+    const uint4* own = reinterpret_cast<const uint4*>(Tp + (int64_t)s * rw);
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+        const int q = c * 256 + tid;
+        old[c] = (q < n4) ? __ldg(own + q) : make_uint4(0u, 0u, 0u, 0u);
+        acc[c] = old[c];
+    }
+    constexpr int NB = (CHUNKS >= 4) ? 2 : (CHUNKS == 2 ? 4 : 8);     // neighbours in flight: 8 uint4 loads per thread
+    const int e0 = __ldg(p.rowptr + s), e1 = __ldg(p.rowptr + s + 1);
+    int e = e0;
+    for (; e + NB <= e1; e += NB) {
+        const uint4* nbr[NB];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) nbr[b] = reinterpret_cast<const uint4*>(Tp + (int64_t)__ldg(col + e + b) * rw);
+        uint4 x[NB][CHUNKS];
+#pragma unroll
+        for (int b = 0; b < NB; ++b)
+#pragma unroll
+            for (int c = 0; c < CHUNKS; ++c) {
+                const int q = c * 256 + tid;
+                x[b][c] = (q < n4) ? __ldg(nbr[b] + q) : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+        for (int b = 0; b < NB; ++b)
+#pragma unroll
+            for (int c = 0; c < CHUNKS; ++c) {
+                acc[c].x |= x[b][c].x; acc[c].y |= x[b][c].y; acc[c].z |= x[b][c].z; acc[c].w |= x[b][c].w;
+            }
+    }
+    for (; e < e1; ++e) {
+        const uint4* nb = reinterpret_cast<const uint4*>(Tp + (int64_t)__ldg(col + e) * rw);
+#pragma unroll
+        for (int c = 0; c < CHUNKS; ++c) {
+            const int q = c * 256 + tid;
+            if (q < n4) {
+                const uint4 x = __ldg(nb + q);
+                acc[c].x |= x.x; acc[c].y |= x.y; acc[c].z |= x.z; acc[c].w |= x.w;
+            }
+        }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(Tn + (int64_t)s * rw);
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+        const int q = c * 256 + tid;
+        if (q < n4) dst[q] = acc[c];
+    }
+    const int64_t row = row_of_node ? (int64_t)__ldg(row_of_node + s) : (int64_t)__ldg(p.out_rows + blockIdx.x);
+    if (row < 0) return;                          // not a requested source (uniform over the CTA)
+    uint32_t* Fn = rc_smem;
+    uint32_t* P = rc_smem + rw;
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+        const int q = c * 256 + tid;
+        if (q < n4)
+            *reinterpret_cast<uint4*>(Fn + 4 * q) =
+                make_uint4(acc[c].x & ~old[c].x, acc[c].y & ~old[c].y, acc[c].z & ~old[c].z, acc[c].w & ~old[c].w);
+    }
+    __syncthreads();
+    ring_outputs<256>(p, s, row, p.h, Fn, P, warp_tot);
+}
+
+// row_of_node[s] = output row of source s (the table is pre-filled with -1)
+__global__ void row_of_node_kernel(const int32_t* __restrict__ srcs, const int32_t* __restrict__ out_rows, int n_src,
+                                   int32_t* __restrict__ row_of_node) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_src) row_of_node[srcs[i]] = out_rows[i];
+}
+
 static inline int64_t dense_row_words(int32_t n_nodes) { return ((int64_t)(n_nodes + 31) / 32 + 3) / 4 * 4; }
 
 }  // namespace hsd
 
 extern "C" int64_t hsd_ring_dense_workspace_words(int32_t n_nodes) {
-    return 2 * (int64_t)n_nodes * hsd::dense_row_words(n_nodes);
+    // two N x N-bit tables + the node -> output row map of the fused level kernel
+    return 2 * (int64_t)n_nodes * hsd::dense_row_words(n_nodes) + ((int64_t)n_nodes + 3) / 4 * 4;
 }
 
 extern "C" int hsd_ring_signature_degree_dense(const int32_t* rowptr, const int32_t* col, int32_t n_nodes,
@@ -199,7 +295,7 @@ extern "C" int hsd_ring_signature_degree_dense(const int32_t* rowptr, const int3
         HSD_REQUIRE(sig_ld >= 1 + (int64_t)hops * (n_bins - 1), "sig_ld too small");
     }
     const int64_t rw = dense_row_words(n_nodes);
-    HSD_REQUIRE(workspace_words >= 2 * (int64_t)n_nodes * rw, "workspace smaller than hsd_ring_dense_workspace_words");
+    HSD_REQUIRE(workspace_words >= hsd_ring_dense_workspace_words(n_nodes), "workspace smaller than hsd_ring_dense_workspace_words");
     HSD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "workspace must be 16-byte aligned");
     if (n_src == 0) return HSD_OK;
     const int nw = (n_nodes + 31) / 32;
@@ -224,16 +320,43 @@ extern "C" int hsd_ring_signature_degree_dense(const int32_t* rowptr, const int3
     ring_cdf_kernel<256><<<n_src, 256, smem, stream>>>(a);
     HSD_CUDA_TRY(cudaGetLastError());
     const unsigned chunks = (unsigned)((rw / 4 + 255) / 256);
+    // rows of 1025..4096 words (32k < N <= 131k nodes): the OR pass and the CDF pass of a level are one kernel,
+    // which saves re-reading both rows from HBM (C3: 8.7 -> 7.7 ms).  Shorter rows are L2-resident and measured
+    // faster as two lean kernels (C2: 0.36 vs 0.40 ms fused); longer rows do not fit the register budget.
+    const bool fused = chunks >= 2 && chunks <= 4;
+    int32_t* row_of_node = reinterpret_cast<int32_t*>(workspace + 2 * (int64_t)n_nodes * rw);
+    if (fused && hops > 2) {
+        HSD_CUDA_TRY(cudaMemsetAsync(row_of_node, 0xff, (size_t)n_nodes * sizeof(int32_t), stream));
+        row_of_node_kernel<<<(n_src + 255) / 256, 256, 0, stream>>>(src_nodes, out_rows, n_src, row_of_node);
+        HSD_CUDA_TRY(cudaGetLastError());
+    }
+    auto launch_fused = [&](int grid, const int32_t* srcs, const int32_t* rmap, const uint32_t* Tp, uint32_t* Tn) -> int {
+        if (chunks == 2) {
+            HSD_CUDA_TRY(cudaFuncSetAttribute(ball_or_cdf_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ball_or_cdf_kernel<2><<<grid, 256, smem, stream>>>(col, n_nodes, srcs, rmap, Tp, Tn, a);
+        } else {
+            HSD_CUDA_TRY(cudaFuncSetAttribute(ball_or_cdf_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ball_or_cdf_kernel<4><<<grid, 256, smem, stream>>>(col, n_nodes, srcs, rmap, Tp, Tn, a);
+        }
+        HSD_CUDA_TRY(cudaGetLastError());
+        return HSD_OK;
+    };
     for (int h = 2; h <= hops; ++h) {
         const uint32_t* Tp = T[h & 1];        // h = 2 reads T[0]
         uint32_t* Tn = T[(h + 1) & 1];
+        a.h = h; a.cur = Tn; a.prev = Tp;
+        if (fused) {
+            const int rc = (h < hops) ? launch_fused(n_nodes, nullptr, row_of_node, Tp, Tn)
+                                      : launch_fused(n_src, src_nodes, nullptr, Tp, Tn);
+            if (rc != HSD_OK) return rc;
+            continue;
+        }
         if (h < hops) {
             ball_or_kernel<<<dim3(n_nodes, chunks), 256, 0, stream>>>(rowptr, col, n_nodes, nullptr, rw, Tp, Tn);
         } else {
             ball_or_kernel<<<dim3(n_src, chunks), 256, 0, stream>>>(rowptr, col, n_nodes, src_nodes, rw, Tp, Tn);
         }
         HSD_CUDA_TRY(cudaGetLastError());
-        a.h = h; a.cur = Tn; a.prev = Tp;
         ring_cdf_kernel<256><<<n_src, 256, smem, stream>>>(a);
         HSD_CUDA_TRY(cudaGetLastError());
     }

@@ -155,7 +155,7 @@ def ensure_bfs_workspace(n_nodes: int, device) -> None:
 _DENSE_WS = {}   # device index -> int32 workspace tensor (grow-only) of the dense ring variant
 
 
-def ring_algorithm(n_nodes: int, n_src: int, hops: int, device) -> str:
+def ring_algorithm(n_nodes: int, n_src: int, hops: int, device, distinct: bool = True) -> str:
     """'dense' (hsd_ring_signature_degree_dense: bitmap dynamic programming over all nodes) or 'frontier'
     (hsd_ring_signature_degree: one frontier-expansion BFS per source).  Dense pays O(E N / 32) per level
     for ALL nodes at the intermediate levels, so it is chosen when at least a fifth of the nodes are
@@ -165,6 +165,8 @@ def ring_algorithm(n_nodes: int, n_src: int, hops: int, device) -> str:
     import os
     force = os.environ.get("HSD_RING_ALGO", "")
     if hops < 1 or (n_nodes + 31) // 32 * 8 > 200 * 1024:
+        return "frontier"
+    if not distinct:          # the dense variant emits one output row per node: sources must be distinct
         return "frontier"
     if force in ("dense", "frontier"):
         return force
@@ -194,11 +196,11 @@ def dense_ring_workspace(n_nodes: int, device) -> torch.Tensor:
 
 def launch_ring_signature(dg_rowptr, dg_col, n, nnz, src, out_rows, n_src, hops, bin_end, delta, n_bins,
                           sig, ld, sizes, bitmaps, empty_as_zero, status, device, peers=None, threads=0,
-                          stream=None) -> str:
+                          stream=None, distinct: bool = True) -> str:
     """One call site for the K1/K2 entry points: picks the dense or the frontier variant (same outputs,
     bit for bit) and launches it on `stream` (default: the current stream).  Returns the variant used."""
     stream = _stream() if stream is None else stream
-    algo = ring_algorithm(n, n_src, hops, device)
+    algo = ring_algorithm(n, n_src, hops, device, distinct)
     n_peers = int(peers.numel()) if peers is not None else 0
     if algo == "dense":
         ws = dense_ring_workspace(n, device)
@@ -252,8 +254,10 @@ def ring_signature_degree(dg: DeviceGraph, hops: int, rows: Optional[torch.Tenso
     bitmaps = (torch.empty((n_src, hops + 1, dg.n_words), dtype=torch.int32, device=dev)
                if want_bitmaps else None)
     status = torch.zeros(1, dtype=torch.int32, device=dev)
+    distinct = rows is None or int(torch.unique(rows).numel()) == n_src
     launch_ring_signature(dg.rowptr, dg.col, dg.n, dg.nnz, src, out_rows, n_src, hops, dg.bin_end, dg.delta,
-                          dg.n_bins, sig, ld, sizes, bitmaps, 1 if empty == "zero" else 0, status, dev)
+                          dg.n_bins, sig, ld, sizes, bitmaps, 1 if empty == "zero" else 0, status, dev,
+                          distinct=distinct)
     return sig, sizes, bitmaps, status
 
 

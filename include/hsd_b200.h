@@ -103,7 +103,8 @@ int hsd_ring_signature_degree_allgather(const int32_t* rowptr, const int32_t* co
  * nullable).  Intermediate levels are computed for all n_nodes nodes whatever n_src is, and the cost is
  * O(E N / 32) per level whatever the ball sizes: the host picks this variant when most nodes are sources
  * and the workspace fits.  workspace: hsd_ring_dense_workspace_words(n_nodes) uint32 words (two N x N-bit
- * tables), 16-byte aligned, caller-owned; nnz = rowptr[n_nodes]; hops >= 1. */
+ * tables + a node -> output-row map), 16-byte aligned, caller-owned; nnz = rowptr[n_nodes]; hops >= 1;
+ * src_nodes must be DISTINCT (the fused level kernel emits one output row per node). */
 int64_t hsd_ring_dense_workspace_words(int32_t n_nodes);
 int hsd_ring_signature_degree_dense(const int32_t* rowptr, const int32_t* col, int32_t n_nodes,
                                     const int32_t* src_nodes, const int32_t* out_rows, int32_t n_src,

@@ -148,3 +148,18 @@ def test_dense_and_frontier_ring_variants_agree_bitwise(n, m, hops, monkeypatch)
             if x is not None:
                 assert torch.equal(x, y)
     assert int(out["dense"][1][3].item()) & 1                      # isolated nodes raise the empty-ring flag
+
+
+def test_repeated_sources_fall_back_to_the_frontier_variant(monkeypatch):
+    """The dense variant emits one output row per node; a caller-supplied source list with repeats
+    must still fill every output row (the dispatcher keeps it on the frontier kernel)."""
+    import torch
+    from hsd_b200 import engine
+    from hsd_b200.graph import powerlaw_graph
+    g = powerlaw_graph(900, 4, seed=1)
+    dg = engine.DeviceGraph.upload(g)
+    monkeypatch.setenv("HSD_RING_ALGO", "dense")
+    rows = torch.arange(900, dtype=torch.int32, device="cuda").repeat_interleave(2)[:1500]
+    sig, sizes, _, _ = engine.ring_signature_degree(dg, 3, rows=rows)
+    ref_sig, ref_sizes, _, _ = engine.ring_signature_degree(dg, 3)
+    assert torch.equal(sig, ref_sig[rows.long()]) and torch.equal(sizes, ref_sizes[rows.long()])

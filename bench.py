@@ -417,7 +417,10 @@ def measure_degree_path(ctx, g, hops, steps, warmup, workload_key):
     rec = {"ms_per_step": ms_per_step, "value": value, "pairs": pairs, "peer": peer, "k_alg": k_alg,
            "n_bins": dg.n_bins, "stage_ms": {"bfs_signature": bfs_ms, "allgather_transpose": gather_ms, "pairwise": pair_ms},
            "roofline": roofline, "roofline_bfs": roofline_bfs, "clocks": clocks,
-           "launches_per_step": (3 if plan.n_rows else 2) + (2 * hops if variant == "dense" else 0)}
+           # ring phase: scatter + hops CDF passes + (hops - 1) OR passes (dense, unfused; the fused build for 32k < N <= 131k
+           # launches hops + 2), or one BFS kernel (two with the hub split); then transpose + pairwise
+           "launches_per_step": ((2 * hops if n <= 32768 or n > 131072 else hops + 2) if variant == "dense"
+                                 else (2 if plan.hub_split is not None else 1)) + (2 if plan.n_rows else 1)}
     return rec, plan, dg
 
 
@@ -433,6 +436,45 @@ def workload_config(n, hops, world, peer, n_bins):
                 "(fused all-gather, no collective); symmetric tiles dealt round-robin to ranks and mirrored "
                 "into the owners' row blocks through peer memory (torch symmetric memory allocations)" if peer else
                 "independent row blocks (every rank computes rows x all columns); one NCCL all-gather")}
+
+
+def extra_c1(ctx):
+    """BASELINE config 1: model/HSD.py 3-hop distance matrix on the bundled airport graphs through the
+    reference-faithful wavelet signal (exact heat kernel, FP64, scipy-W1 semantics), checked against rows /
+    the full matrix the UNMODIFIED reference produced (tests/golden/reference_runs.npz; reference CPU
+    times measured at survey time on one core: europe 18.1 s, usa 256.2 s)."""
+    torch = ctx.torch
+    import networkx as nx
+    from model import HSD
+    gz = np.load(os.path.join(ROOT, "tests", "golden", "graphs.npz"))
+    runs = np.load(os.path.join(ROOT, "tests", "golden", "reference_runs.npz"))
+    out = []
+    for name in ("europe", "usa"):
+        nodes = [str(v) for v in gz[f"{name}_nodes"]]
+        G = nx.Graph()
+        G.add_nodes_from(nodes)
+        G.add_edges_from((nodes[u], nodes[v]) for u, v in gz[f"{name}_edges"])
+        hop, scale = int(runs[f"{name}_hop"]), float(runs[f"{name}_scale"])
+        m = HSD(G, name, scale, hop, "wasserstein", device=ctx.dev)
+        m.calculate_structural_distance(scale, approx=False)           # warm-up (cuSOLVER handles, rings)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        D = m.calculate_structural_distance(scale, approx=False)        # float64 ndarray on the host, like the reference
+        wall = time.perf_counter() - t0
+        n = m.n_node
+        if name == "europe":
+            ref, got = np.asarray(runs["europe_D"]).reshape(n, n), D
+        else:
+            ref, got = runs["usa_Drows"], D[runs["usa_rows"]]
+        err = float(np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-9 * np.abs(ref).max())))
+        out.append({"graph": name, "n_nodes": n, "hops": hop, "scale": scale, "ms": wall * 1e3,
+                    "node_pairs_per_s": n * (n - 1) / 2 / wall, "max_rel_err_vs_reference_output": err,
+                    "reference_cpu_s_one_core_survey": {"europe": 18.1, "usa": 256.2}[name]})
+        del m
+    return {"workload": "bundled airport graphs, exact heat-kernel wavelet signal, 3 hops (model/HSD.py:98-114)",
+            "dtype": "f64", "cases": out,
+            "note": "wall time of HSD.calculate_structural_distance(scale, approx=False) incl. eigh (cuSOLVER), "
+                    "the fused wavelet kernel, ring gather + sort, the W1 merge kernel and the copy of the float64 matrix to the host"}
 
 
 def extra_c4(ctx):
@@ -639,6 +681,9 @@ def run_native(args):
                     "clocks": r3["clocks"]}
                 del p3, d3, g3
                 torch.cuda.empty_cache()
+            elif key == "c1":
+                if rank == 0:
+                    extras["c1"] = extra_c1(ctx)
             elif key == "c4":
                 extras["c4"] = extra_c4(ctx)
             elif key == "c5":
@@ -682,7 +727,7 @@ def main():
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-peer", action="store_true", help="N>1: independent row blocks instead of peer-memory mirroring")
-    ap.add_argument("--extras", default="c3,c4,c5",
+    ap.add_argument("--extras", default="c1,c3,c4,c5",
                     help="other BASELINE.json configs measured after the headline workload, as sub-records of the line")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg (NVLink byte-count runs)")

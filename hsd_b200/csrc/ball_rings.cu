@@ -308,6 +308,15 @@ extern "C" int hsd_ring_signature_degree_dense(const int32_t* rowptr, const int3
     a.sig_peers = sig_peers; a.n_peers = n_peers; a.ring_sizes = ring_sizes; a.ring_bitmaps = ring_bitmaps;
     a.empty_as_zero = empty_as_zero; a.status = status;
     HSD_CUDA_TRY(cudaFuncSetAttribute(ring_cdf_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HSD_CUDA_TRY(cudaFuncSetAttribute(ring_cdf_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // short rows (<= 1024 words): the CDF pass is bound by per-CTA fixed instruction work (block scan, bin loop:
+    // 80 % issue-active at C2), which 128-thread CTAs halve
+    auto launch_cdf = [&]() -> int {
+        if (nw <= 1024) ring_cdf_kernel<128><<<n_src, 128, smem, stream>>>(a);
+        else ring_cdf_kernel<256><<<n_src, 256, smem, stream>>>(a);
+        HSD_CUDA_TRY(cudaGetLastError());
+        return HSD_OK;
+    };
     HSD_REQUIRE(hops >= 1, "the dense variant needs hops >= 1 (hop 0 alone: use hsd_ring_signature_degree)");
     // ---- ball_1 ----
     HSD_CUDA_TRY(cudaMemsetAsync(T[0], 0, (size_t)n_nodes * rw * sizeof(uint32_t), stream));
@@ -317,8 +326,7 @@ extern "C" int hsd_ring_signature_degree_dense(const int32_t* rowptr, const int3
         HSD_CUDA_TRY(cudaGetLastError());
     }
     a.h = 1; a.cur = T[0]; a.prev = nullptr;
-    ring_cdf_kernel<256><<<n_src, 256, smem, stream>>>(a);
-    HSD_CUDA_TRY(cudaGetLastError());
+    { const int rc = launch_cdf(); if (rc != HSD_OK) return rc; }
     const unsigned chunks = (unsigned)((rw / 4 + 255) / 256);
     // rows of 1025..4096 words (32k < N <= 131k nodes): the OR pass and the CDF pass of a level are one kernel,
     // which saves re-reading both rows from HBM (C3: 8.7 -> 7.7 ms).  Shorter rows are L2-resident and measured
@@ -351,14 +359,15 @@ extern "C" int hsd_ring_signature_degree_dense(const int32_t* rowptr, const int3
             if (rc != HSD_OK) return rc;
             continue;
         }
+        // a thread owns one 16-byte piece of the row: rows shorter than 1024 words get narrower CTAs (no idle warps)
+        const int or_threads = chunks == 1 ? (int)std::min<int64_t>(256, (rw / 4 + 31) / 32 * 32) : 256;
         if (h < hops) {
-            ball_or_kernel<<<dim3(n_nodes, chunks), 256, 0, stream>>>(rowptr, col, n_nodes, nullptr, rw, Tp, Tn);
+            ball_or_kernel<<<dim3(n_nodes, chunks), or_threads, 0, stream>>>(rowptr, col, n_nodes, nullptr, rw, Tp, Tn);
         } else {
-            ball_or_kernel<<<dim3(n_src, chunks), 256, 0, stream>>>(rowptr, col, n_nodes, src_nodes, rw, Tp, Tn);
+            ball_or_kernel<<<dim3(n_src, chunks), or_threads, 0, stream>>>(rowptr, col, n_nodes, src_nodes, rw, Tp, Tn);
         }
         HSD_CUDA_TRY(cudaGetLastError());
-        ring_cdf_kernel<256><<<n_src, 256, smem, stream>>>(a);
-        HSD_CUDA_TRY(cudaGetLastError());
+        { const int rc = launch_cdf(); if (rc != HSD_OK) return rc; }
     }
     return HSD_OK;
 }

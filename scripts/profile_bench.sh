@@ -7,5 +7,5 @@ $CMD > gpurun_out/plain_${TAG}.log 2> gpurun_out/plain_${TAG}.err &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${TAG}.csv $CMD > gpurun_out/ncu_launch_${TAG}.log 2>&1
 echo "launch list rc=$?"
 python scripts/time_c2.py 20000 3 > gpurun_out/plain_c2_${TAG}.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'pairwise_l1|bfs_ring' -s 2 -c 2 -f -o gpurun_out/prof_${TAG} python scripts/time_c2.py 20000 3 > gpurun_out/ncu_full_${TAG}.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'pairwise_l1|bfs_ring|ball_or|ring_cdf' -s 7 -c 7 -f -o gpurun_out/prof_${TAG} python scripts/time_c2.py 20000 3 > gpurun_out/ncu_full_${TAG}.log 2>&1
 echo "full capture rc=$?"

@@ -158,8 +158,8 @@ _DENSE_WS = {}   # device index -> int32 workspace tensor (grow-only) of the den
 def ring_algorithm(n_nodes: int, n_src: int, hops: int, device, distinct: bool = True) -> str:
     """'dense' (hsd_ring_signature_degree_dense: bitmap dynamic programming over all nodes) or 'frontier'
     (hsd_ring_signature_degree: one frontier-expansion BFS per source).  Dense pays O(E N / 32) per level
-    for ALL nodes at the intermediate levels, so it is chosen when at least a fifth of the nodes are
-    sources (measured break-even: a rank of a 4-GPU job still gains, a rank of an 8-GPU job does not; HSD_RING_DENSE_MIN_FRAC), hops >= 2 and its two N x N-bit tables fit
+    for ALL nodes at the intermediate levels, so it is chosen when at least a fifth (a tenth from 64k nodes)
+    of the nodes are sources (HSD_RING_DENSE_MIN_FRAC), hops >= 2 and its two N x N-bit tables fit
     in a quarter of the free device memory.  HSD_RING_ALGO=dense|frontier overrides
     (dense still needs hops >= 1)."""
     import os
@@ -170,7 +170,10 @@ def ring_algorithm(n_nodes: int, n_src: int, hops: int, device, distinct: bool =
         return "frontier"
     if force in ("dense", "frontier"):
         return force
-    min_frac = float(os.environ.get("HSD_RING_DENSE_MIN_FRAC", "0.2"))
+    # measured break-even per rank of a W-way split (scripts/time_shard_bfs.py, profiles/r2_rings_notes.md):
+    # 20k nodes: dense wins up to W = 4 (0.177 vs 0.186 ms) and loses at W = 8 (0.170 vs 0.132: latency-bound);
+    # 100k nodes: dense still wins at W = 8 (4.9 vs 5.3 ms)
+    min_frac = float(os.environ.get("HSD_RING_DENSE_MIN_FRAC", "0.2" if n_nodes < 65536 else "0.1"))
     if hops < 2 or n_src < min_frac * n_nodes or n_nodes < 512:
         return "frontier"
     words = int(lib.hsd_ring_dense_workspace_words(n_nodes))

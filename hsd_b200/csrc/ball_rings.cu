@@ -289,6 +289,7 @@ extern "C" int hsd_ring_signature_degree_dense(const int32_t* rowptr, const int3
     cudaStream_t stream = (cudaStream_t)stream_;
     HSD_REQUIRE(rowptr && col && src_nodes && out_rows && workspace, "null pointer");
     HSD_REQUIRE(n_nodes > 0 && n_src >= 0 && hops >= 0 && nnz >= 0, "bad sizes");
+    HSD_REQUIRE(hops >= 1, "the dense variant needs hops >= 1 (hop 0 alone: use hsd_ring_signature_degree)");
     HSD_REQUIRE(n_peers >= 0 && n_peers <= 64 && (n_peers == 0 || (sig && sig_peers)), "bad peer list");
     if (sig) {
         HSD_REQUIRE(bin_end && delta && n_bins >= 1 && status, "sig requested without support tables");
@@ -317,7 +318,6 @@ extern "C" int hsd_ring_signature_degree_dense(const int32_t* rowptr, const int3
         HSD_CUDA_TRY(cudaGetLastError());
         return HSD_OK;
     };
-    HSD_REQUIRE(hops >= 1, "the dense variant needs hops >= 1 (hop 0 alone: use hsd_ring_signature_degree)");
     // ---- ball_1 ----
     HSD_CUDA_TRY(cudaMemsetAsync(T[0], 0, (size_t)n_nodes * rw * sizeof(uint32_t), stream));
     {

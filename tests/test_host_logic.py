@@ -41,6 +41,18 @@ def test_c_abi_argument_validation_without_gpu():
     assert lib.hsd_topk_rows(p, 4, 4, 8, 2, 0, None, p, p, None) == -1               # ld >= n_cols
     assert lib.hsd_scatter_symmetric(None, 8, 2, 8, p, p, 8, 1, None) == -1 and b"null" in lib.hsd_last_error_string()
     assert lib.hsd_scatter_symmetric(p, 4, 2, 8, p, p, 8, 1, None) == -1             # blk_ld >= n
+    # round-2 entry points
+    assert lib.hsd_exact_wavelets(None, 4, p, 4, 1.0, 0.0, 1, p, 4, None) == -1 and b"null" in lib.hsd_last_error_string()
+    assert lib.hsd_exact_wavelets(p, 2, p, 4, 1.0, 0.0, 1, p, 4, None) == -1          # ldu >= n
+    assert lib.hsd_copy2d_to_host(None, 16, p, 16, 16, 1, None) == -1
+    assert lib.hsd_copy2d_to_host(p, 8, p, 16, 16, 1, None) == -1                    # pitch >= width
+    assert lib.hsd_copy2d_to_host(p, 16, p, 16, 0, 0, None) == 0                     # empty window: nothing to do
+    words = lib.hsd_ring_dense_workspace_words(1000)
+    assert words == 2 * 1000 * 32 + 1000                                            # two 1000 x 1024-bit tables + the row map
+    assert lib.hsd_ring_signature_degree_dense(p, p, 1000, p, p, 10, 2, p, p, 3, p, 8, None, 0, p, None, 0, p,
+                                               p, words - 1, 5000, None) == -1       # workspace too small
+    assert lib.hsd_ring_signature_degree_dense(p, p, 1000, p, p, 10, 0, p, p, 3, p, 8, None, 0, p, None, 0, p,
+                                               p, words, 5000, None) == -1 and b"hops >= 1" in lib.hsd_last_error_string()
     # graphs whose four N-bit bitmaps fit shared memory need no BFS workspace; larger ones say how much
     assert lib.hsd_bfs_workspace_words(100000) == 0
     words = lib.hsd_bfs_workspace_words(450000)

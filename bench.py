@@ -380,8 +380,20 @@ def measure_degree_path(ctx, g, hops, steps, warmup, workload_key):
     }
     # ---- secondary: ring + signature phase against HBM/L2 ----
     own = slice(plan.rank * plan.per, plan.rank * plan.per + plan.n_src)   # this rank's sources in the table
-    variant = engine.ring_algorithm(n, plan.n_src, hops, dev)
-    if variant == "dense":
+    variant = "cols" if getattr(plan, "ring_mode", "rows") == "cols" else engine.ring_algorithm(n, plan.n_src, hops, dev)
+    if variant == "cols":
+        # column-split dense variant: every level for all nodes on 1/world of the bitmap words, then one integer
+        # all-reduce of the partial counts (N x (hops (B-1) + hops) int32) and the signature build for all nodes
+        row_b = ((n + 31) // 32 + 3) // 4 * 4 * 4.0 / world
+        nnz = float(dg.nnz)
+        ring_bytes = 2 * n * row_b + (hops - 1) * ((nnz + n) * row_b + n * row_b + 2 * n * row_b)
+        counts_b = 4.0 * n * (hops * (dg.n_bins - 1) + hops)
+        ring_bytes += hops * counts_b / hops + 2 * counts_b + 4.0 * k_alg * n      # counts written, all-reduced, read; table written
+        ring_kernel = "ball_or_kernel + ring_count_cols_kernel + signature_from_counts_kernel (column-split dense variant) + NCCL all-reduce of the counts"
+        ring_note = (f"each rank runs the bitmap recursion for all nodes on 1/{world} of the bitmap columns; "
+                     f"{counts_b/1e6:.0f} MB of int32 partial counts are summed by one all-reduce")
+        edges_scanned = None
+    elif variant == "dense":
         # bitmap dynamic programming: level h >= 2 reads (entries + rows) N-bit rows of the previous table and
         # writes one row per computed node; intermediate levels cover all nodes, the last one this rank's sources
         row_b = ((n + 31) // 32 + 3) // 4 * 4 * 4.0
@@ -419,7 +431,8 @@ def measure_degree_path(ctx, g, hops, steps, warmup, workload_key):
            "roofline": roofline, "roofline_bfs": roofline_bfs, "clocks": clocks,
            # ring phase: scatter + hops CDF passes + (hops - 1) OR passes (dense, unfused; the fused build for 32k < N <= 131k
            # launches hops + 2), or one BFS kernel (two with the hub split); then transpose + pairwise
-           "launches_per_step": ((2 * hops if n <= 32768 or n > 131072 else hops + 2) if variant == "dense"
+           "launches_per_step": ((2 * hops + 1) if variant == "cols" else
+                                 (2 * hops if n <= 32768 or n > 131072 else hops + 2) if variant == "dense"
                                  else (2 if plan.hub_split is not None else 1)) + (2 if plan.n_rows else 1)}
     return rec, plan, dg
 

@@ -18,6 +18,7 @@ HEADER_SYMBOLS = [
     "hsd_signature_transpose", "hsd_scatter_symmetric", "hsd_pairwise_l1", "hsd_pairwise_l1_sharded", "hsd_ring_signature_values",
     "hsd_pairwise_w1_merge", "hsd_pairwise_aligned", "hsd_pairwise_worker", "hsd_cheb_spmm", "hsd_laplacian_spmv", "hsd_ring_reduce", "hsd_characteristic_function", "hsd_topk_rows",
     "hsd_fp32_peak_probe", "hsd_copy2d_to_host", "hsd_mirror_upper_to_lower_host", "hsd_exact_wavelets", "hsd_ring_dense_workspace_words", "hsd_ring_signature_degree_dense",
+    "hsd_ring_cols_workspace_words", "hsd_ring_counts_dense_cols", "hsd_ring_signature_from_counts",
 ]
 
 
@@ -48,6 +49,11 @@ lib.hsd_ring_signature_degree_allgather.argtypes = [_P, _P, c_int32, _P, _P, c_i
                                                     _P, c_int64, _P, c_int32, _P, c_int32, _P, c_int32, _P]
 lib.hsd_bfs_workspace_words.argtypes = [c_int32]
 lib.hsd_ring_dense_workspace_words.argtypes = [c_int32]
+lib.hsd_ring_cols_workspace_words.argtypes = [c_int32, c_int32, c_int32]
+lib.hsd_ring_counts_dense_cols.argtypes = [_P, _P, c_int32, c_int64, c_int32, _P, c_int32, c_int32, c_int32, _P, c_int64,
+                                           _P, c_int64, _P]
+lib.hsd_ring_signature_from_counts.argtypes = [_P, _P, c_int64, _P, _P, c_int32, c_int32, _P, c_int32, _P, c_int64,
+                                               _P, c_int32, _P, _P]
 lib.hsd_ring_signature_degree_dense.argtypes = [_P, _P, c_int32, _P, _P, c_int32, c_int32, _P, _P, c_int32,
                                                 _P, c_int64, _P, c_int32, _P, _P, c_int32, _P, _P, c_int64, c_int64, _P]
 lib.hsd_bfs_set_workspace.argtypes = [_P, c_int64]
@@ -76,10 +82,12 @@ lib.hsd_exact_wavelets.argtypes = [_P, c_int64, _P, c_int32, c_double, c_double,
 lib.hsd_copy2d_to_host.argtypes = [_P, c_int64, _P, c_int64, c_int64, c_int64, _P]
 lib.hsd_mirror_upper_to_lower_host.argtypes = [_P, c_int64, c_int32, c_int32, c_int32, c_int32]
 for _name in HEADER_SYMBOLS:
-    if _name not in ("hsd_last_error_string", "hsd_bfs_workspace_words", "hsd_ring_dense_workspace_words"):
+    if _name not in ("hsd_last_error_string", "hsd_bfs_workspace_words", "hsd_ring_dense_workspace_words",
+                     "hsd_ring_cols_workspace_words"):
         getattr(lib, _name).restype = c_int32
 lib.hsd_bfs_workspace_words.restype = c_int64
 lib.hsd_ring_dense_workspace_words.restype = c_int64
+lib.hsd_ring_cols_workspace_words.restype = c_int64
 
 
 class HSDError(RuntimeError):

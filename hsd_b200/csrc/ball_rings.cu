@@ -268,6 +268,124 @@ __global__ void row_of_node_kernel(const int32_t* __restrict__ srcs, const int32
     if (i < n_src) row_of_node[srcs[i]] = out_rows[i];
 }
 
+// ---- column-split dense variant (several GPUs) -----------------------------------------------------
+// The OR recursion is independent per bitmap word, so rank r of W can run EVERY level for ALL nodes on
+// its own range of bitmap words [w_begin, w_begin + lw) with no exchange at all (tables of N x lw words,
+// 1/W of the work and of the memory).  What a rank cannot do alone is the prefix popcount of a ring over
+// the whole row; it emits the PARTIAL integer counts of its word range,
+//   counts[s][(h-1)*(B-1) + b] = #{ j in ring_h(s) : w_begin*32 <= j < min(bin_end[b], (w_begin+lw)*32) }
+//   counts[s][hops*(B-1) + h-1] = #{ j in ring_h(s) in the word range }              (partial ring size)
+// the host sums them over the ranks (one integer all-reduce: exact, order-free) and
+// signature_from_counts_kernel applies the same float arithmetic as the other variants to the sums, so
+// the signatures are bit-identical to the single-GPU ones.
+__global__ void __launch_bounds__(256)
+ball1_scatter_cols_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int n, int64_t nnz,
+                          int lw, int w_begin, uint32_t* __restrict__ T) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < n) {
+        const int w = (int)(idx >> 5) - w_begin;
+        if (w >= 0 && w < lw) atomicOr(T + idx * lw + w, 1u << (idx & 31));
+    }
+    if (idx >= nnz) return;
+    const int u = __ldg(col + idx);
+    const int w = (u >> 5) - w_begin;
+    if (w < 0 || w >= lw) return;
+    int lo = 0, hi = n;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if ((int64_t)__ldg(rowptr + mid) <= idx) lo = mid; else hi = mid;
+    }
+    atomicOr(T + (int64_t)lo * lw + w, 1u << (u & 31));
+}
+
+struct RingCountArgs {
+    int32_t n_nodes, lw, w_begin, hops, h, n_bins;
+    const uint32_t* cur;
+    const uint32_t* prev;      // nullptr at h = 1 (the ring is ball_1 minus the node itself)
+    const int32_t* bin_end;
+    int32_t* counts;
+    int64_t ld_c;
+};
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+ring_count_cols_kernel(const RingCountArgs p) {
+    extern __shared__ __align__(16) uint32_t rc_smem[];
+    __shared__ int warp_tot[THREADS / 32];
+    uint32_t* Fn = rc_smem;
+    uint32_t* P = rc_smem + p.lw;
+    const int tid = threadIdx.x, lw = p.lw, nb1 = p.n_bins - 1;
+    const int s = blockIdx.x;
+    const uint4* cur4 = reinterpret_cast<const uint4*>(p.cur + (int64_t)s * lw);
+    const uint4* prv4 = p.prev ? reinterpret_cast<const uint4*>(p.prev + (int64_t)s * lw) : nullptr;
+    for (int q = tid; q < lw / 4; q += THREADS) {
+        uint4 c = __ldg(cur4 + q);
+        if (prv4) {
+            const uint4 b = __ldg(prv4 + q);
+            c.x &= ~b.x; c.y &= ~b.y; c.z &= ~b.z; c.w &= ~b.w;
+        }
+        *reinterpret_cast<uint4*>(Fn + 4 * q) = c;
+    }
+    __syncthreads();
+    if (!prv4 && tid == 0) {
+        const int w = (s >> 5) - p.w_begin;
+        if (w >= 0 && w < lw) Fn[w] &= ~(1u << (s & 31));
+    }
+    __syncthreads();
+    const int cpt = (lw + THREADS - 1) / THREADS;
+    const int w_lo = min(tid * cpt, lw), w_hi = min(w_lo + cpt, lw);
+    int local = 0;
+    for (int w = w_lo; w < w_hi; ++w) local += __popc(Fn[w]);
+    int n_part;
+    int run = block_exclusive_scan<THREADS>(local, warp_tot, &n_part);
+    for (int w = w_lo; w < w_hi; ++w) {
+        P[w] = (uint32_t)run;
+        run += __popc(Fn[w]);
+    }
+    __syncthreads();
+    int32_t* dst = p.counts + (int64_t)s * p.ld_c;
+    if (tid == 0) dst[p.hops * nb1 + (p.h - 1)] = n_part;
+    const int bit_lo = p.w_begin * 32, bit_hi = bit_lo + lw * 32;
+    for (int b = tid; b < nb1; b += THREADS) {
+        const int e = min(max(__ldg(p.bin_end + b), bit_lo), bit_hi) - bit_lo;     // bits of the local range below bin_end[b]
+        int cnt = n_part;
+        if (e < lw * 32) cnt = (int)P[e >> 5] + __popc(Fn[e >> 5] & ((1u << (e & 31)) - 1u));
+        dst[(p.h - 1) * nb1 + b] = cnt;
+    }
+}
+
+// counts (summed over the word ranges) -> signature rows; one warp per (source, hop) would do, a CTA per
+// source keeps it simple: same arithmetic as ring_outputs.
+__global__ void __launch_bounds__(128)
+signature_from_counts_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ counts, int64_t ld_c,
+                             const int32_t* __restrict__ src_nodes, const int32_t* __restrict__ out_rows,
+                             int hops, const float* __restrict__ delta, int n_bins, float* __restrict__ sig,
+                             int64_t sig_ld, int32_t* __restrict__ ring_sizes, int empty_as_zero,
+                             int32_t* __restrict__ status) {
+    const int s = src_nodes[blockIdx.x];
+    const int64_t row = out_rows[blockIdx.x];
+    const int nb1 = n_bins - 1, hops1 = hops + 1, tid = threadIdx.x;
+    const int32_t* c = counts + (int64_t)s * ld_c;
+    if (tid == 0) {
+        if (sig) sig[row * sig_ld] = (float)(rowptr[s + 1] - rowptr[s]);
+        if (ring_sizes) ring_sizes[row * hops1] = 1;
+    }
+    for (int h = 1; h <= hops; ++h) {
+        const int n_ring = c[hops * nb1 + (h - 1)];
+        if (tid == 0 && ring_sizes) ring_sizes[row * hops1 + h] = n_ring;
+        if (!sig) continue;
+        float* dst = sig + row * sig_ld + 1 + (int64_t)(h - 1) * nb1;
+        if (n_ring > 0) {
+            const float n_f = (float)n_ring;
+            for (int b = tid; b < nb1; b += 128)
+                dst[b] = __fdiv_rn((float)c[(h - 1) * nb1 + b] * __ldg(delta + b), n_f);
+        } else {
+            if (!empty_as_zero && tid == 0) atomicOr(status, 1);
+            for (int b = tid; b < nb1; b += 128) dst[b] = empty_as_zero ? __ldg(delta + b) : 0.f;
+        }
+    }
+}
+
 static inline int64_t dense_row_words(int32_t n_nodes) { return ((int64_t)(n_nodes + 31) / 32 + 3) / 4 * 4; }
 
 }  // namespace hsd
@@ -369,5 +487,78 @@ extern "C" int hsd_ring_signature_degree_dense(const int32_t* rowptr, const int3
         HSD_CUDA_TRY(cudaGetLastError());
         { const int rc = launch_cdf(); if (rc != HSD_OK) return rc; }
     }
+    return HSD_OK;
+}
+
+// ---- column-split dense variant: entry points -------------------------------------------------------
+extern "C" int64_t hsd_ring_cols_workspace_words(int32_t n_nodes, int32_t word4_begin, int32_t word4_end) {
+    return 2 * (int64_t)n_nodes * 4 * (int64_t)(word4_end - word4_begin);
+}
+
+extern "C" int hsd_ring_counts_dense_cols(const int32_t* rowptr, const int32_t* col, int32_t n_nodes, int64_t nnz,
+                                          int32_t hops, const int32_t* bin_end, int32_t n_bins,
+                                          int32_t word4_begin, int32_t word4_end, int32_t* counts, int64_t ld_c,
+                                          uint32_t* workspace, int64_t workspace_words, void* stream_) {
+    using namespace hsd;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    HSD_REQUIRE(rowptr && col && bin_end && counts && workspace, "null pointer");
+    HSD_REQUIRE(n_nodes > 0 && hops >= 1 && n_bins >= 1 && nnz >= 0, "bad sizes");
+    const int64_t rw = dense_row_words(n_nodes);
+    HSD_REQUIRE(word4_begin >= 0 && word4_begin <= word4_end && (int64_t)word4_end * 4 <= rw, "bad word range");
+    HSD_REQUIRE(ld_c >= (int64_t)hops * (n_bins - 1) + hops, "ld_c too small");
+    HSD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "workspace must be 16-byte aligned");
+    const int lw = 4 * (word4_end - word4_begin);
+    HSD_REQUIRE(workspace_words >= 2 * (int64_t)n_nodes * lw, "workspace smaller than hsd_ring_cols_workspace_words");
+    if (lw == 0) {      // a rank without columns (more ranks than 16-byte pieces): all counts are zero
+        HSD_CUDA_TRY(cudaMemsetAsync(counts, 0, (size_t)n_nodes * ld_c * sizeof(int32_t), stream));
+        return HSD_OK;
+    }
+    const size_t smem = (size_t)2 * lw * sizeof(uint32_t);
+    HSD_REQUIRE(smem <= 200 * 1024, "word range too wide for the shared-memory count pass");
+    uint32_t* T[2] = {workspace, workspace + (int64_t)n_nodes * lw};
+    HSD_CUDA_TRY(cudaFuncSetAttribute(ring_count_cols_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HSD_CUDA_TRY(cudaMemsetAsync(T[0], 0, (size_t)n_nodes * lw * sizeof(uint32_t), stream));
+    const int64_t items = std::max<int64_t>(nnz, n_nodes);
+    ball1_scatter_cols_kernel<<<(unsigned)((items + 255) / 256), 256, 0, stream>>>(rowptr, col, n_nodes, nnz, lw,
+                                                                                 4 * word4_begin, T[0]);
+    HSD_CUDA_TRY(cudaGetLastError());
+    RingCountArgs a;
+    a.n_nodes = n_nodes; a.lw = lw; a.w_begin = 4 * word4_begin; a.hops = hops; a.n_bins = n_bins;
+    a.bin_end = bin_end; a.counts = counts; a.ld_c = ld_c;
+    a.h = 1; a.cur = T[0]; a.prev = nullptr;
+    ring_count_cols_kernel<128><<<n_nodes, 128, smem, stream>>>(a);
+    HSD_CUDA_TRY(cudaGetLastError());
+    const unsigned chunks = (unsigned)((lw / 4 + 255) / 256);
+    const int or_threads = chunks == 1 ? (int)std::min<int64_t>(256, (lw / 4 + 31) / 32 * 32) : 256;
+    for (int h = 2; h <= hops; ++h) {
+        const uint32_t* Tp = T[h & 1];
+        uint32_t* Tn = T[(h + 1) & 1];
+        ball_or_kernel<<<dim3(n_nodes, chunks), or_threads, 0, stream>>>(rowptr, col, n_nodes, nullptr, lw, Tp, Tn);
+        HSD_CUDA_TRY(cudaGetLastError());
+        a.h = h; a.cur = Tn; a.prev = Tp;
+        ring_count_cols_kernel<128><<<n_nodes, 128, smem, stream>>>(a);
+        HSD_CUDA_TRY(cudaGetLastError());
+    }
+    return HSD_OK;
+}
+
+extern "C" int hsd_ring_signature_from_counts(const int32_t* rowptr, const int32_t* counts, int64_t ld_c,
+                                              const int32_t* src_nodes, const int32_t* out_rows, int32_t n_src,
+                                              int32_t hops, const float* delta, int32_t n_bins, float* sig,
+                                              int64_t sig_ld, int32_t* ring_sizes, int32_t empty_as_zero,
+                                              int32_t* status, void* stream) {
+    using namespace hsd;
+    HSD_REQUIRE(rowptr && counts && src_nodes && out_rows && status, "null pointer");
+    HSD_REQUIRE(n_src >= 0 && hops >= 1 && n_bins >= 1, "bad sizes");
+    HSD_REQUIRE(ld_c >= (int64_t)hops * (n_bins - 1) + hops, "ld_c too small");
+    if (sig) {
+        HSD_REQUIRE(delta, "sig requested without the support gaps");
+        HSD_REQUIRE(sig_ld >= 1 + (int64_t)hops * (n_bins - 1), "sig_ld too small");
+    }
+    if (n_src == 0) return HSD_OK;
+    signature_from_counts_kernel<<<n_src, 128, 0, (cudaStream_t)stream>>>(rowptr, counts, ld_c, src_nodes, out_rows,
+                                                                        hops, delta, n_bins, sig, sig_ld, ring_sizes,
+                                                                        empty_as_zero, status);
+    HSD_CUDA_TRY(cudaGetLastError());
     return HSD_OK;
 }

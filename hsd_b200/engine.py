@@ -224,6 +224,48 @@ def launch_ring_signature(dg_rowptr, dg_col, n, nnz, src, out_rows, n_src, hops,
     return algo
 
 
+# ---- column-split dense variant (one process per GPU; SURVEY §8 e) ----
+def ring_cols_range(n_nodes: int, rank: int, world: int) -> Tuple[int, int]:
+    """[begin, end) of the 16-byte bitmap pieces rank `rank` of `world` owns."""
+    n4 = ((n_nodes + 31) // 32 + 3) // 4
+    per = (n4 + world - 1) // world
+    q0 = min(rank * per, n4)
+    return q0, min(q0 + per, n4)
+
+
+def ring_counts_cols(dg: DeviceGraph, hops: int, rank: int, world: int,
+                     counts: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Partial prefix counts int32[N, hops*(B-1) + hops] of this rank's bitmap columns for ALL nodes
+    (hsd_ring_counts_dense_cols); rows are degree-order ids.  Sum over the ranks (integer all-reduce),
+    then signature_from_counts."""
+    dev = dg.rowptr.device
+    q0, q1 = ring_cols_range(dg.n, rank, world)
+    ld_c = hops * (dg.n_bins - 1) + hops
+    if counts is None:
+        counts = torch.empty((dg.n, ld_c), dtype=torch.int32, device=dev)
+    words = int(lib.hsd_ring_cols_workspace_words(dg.n, q0, q1))
+    key = ("cols", dev.index if dev.index is not None else torch.cuda.current_device())
+    ws = _DENSE_WS.get(key)
+    if ws is None or ws.numel() < max(words, 4):
+        _DENSE_WS[key] = None
+        ws = torch.empty(max(words, 4), dtype=torch.int32, device=dev)
+        _DENSE_WS[key] = ws
+    check(lib.hsd_ring_counts_dense_cols(_ptr(dg.rowptr), _ptr(dg.col), dg.n, dg.nnz, hops, _ptr(dg.bin_end),
+                                         dg.n_bins, q0, q1, _ptr(counts), counts.stride(0), _ptr(ws), ws.numel(),
+                                         _stream()))
+    return counts
+
+
+def signature_from_counts(dg: DeviceGraph, hops: int, counts: torch.Tensor, src: torch.Tensor,
+                          out_rows: torch.Tensor, sig: Optional[torch.Tensor], sizes: Optional[torch.Tensor],
+                          empty: str, status: torch.Tensor) -> None:
+    """Summed counts -> signature rows / ring sizes / empty-ring flag (hsd_ring_signature_from_counts)."""
+    check(lib.hsd_ring_signature_from_counts(
+        _ptr(dg.rowptr), _ptr(counts), counts.stride(0), _ptr(src), _ptr(out_rows), int(src.numel()), hops,
+        _ptr(dg.delta), dg.n_bins, _ptr(sig), sig.stride(0) if sig is not None else 0, _ptr(sizes),
+        1 if empty == "zero" else 0, _ptr(status), _stream()))
+
+
 def ring_signature_degree(dg: DeviceGraph, hops: int, rows: Optional[torch.Tensor] = None,
                           want_sig: bool = True, want_sizes: bool = True,
                           want_bitmaps: bool = False, empty: str = "raise",

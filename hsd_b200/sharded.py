@@ -126,6 +126,18 @@ class ShardedDegreeHSD:
             self.sig_all = torch.zeros((world * self.per, self.ld), dtype=torch.float32, device=dev)
         self.sigT = engine.alloc_signature_table(self.k_used, n, dev)
         self.side = None
+        # Ring phase across ranks.  "cols": every rank runs the dense bitmap recursion for ALL nodes on its own
+        # 1/world of the bitmap columns (no exchange), the partial integer counts are summed by ONE all-reduce and
+        # every rank builds the whole signature table from the sums — 1/world of the ring work per rank instead
+        # of the intermediate levels being recomputed everywhere.  Needs a real process group and is taken from
+        # 32k nodes (below, the phase is latency-bound and the frontier / dense-by-rows kernels win);
+        # HSD_RING_SHARD_MODE=cols|rows overrides.
+        self.ring_mode = "rows"
+        if world > 1 and peer_blocks is None and peer_tables is None and hops >= 1:
+            import torch.distributed as dist
+            want = os.environ.get("HSD_RING_SHARD_MODE", "cols" if n >= 32768 else "rows")
+            if want == "cols" and dist.is_available() and dist.is_initialized():
+                self.ring_mode = "cols"
         self.update_mode = os.environ.get("HSD_DYN_PEER_MODE", "rows")   # see update_finish()
         self._plan_sources(dg)
         node = torch.arange(n, dtype=torch.int32, device=dev)
@@ -162,6 +174,7 @@ class ShardedDegreeHSD:
         # BFS sources are DEALT round-robin (node s -> rank s % world): contiguous blocks would give
         # one rank all the hubs of a preferential-attachment graph (its BFS then takes 2x longer).
         # Table row of node s in the gathered table: (s % world) * per + s // world.
+        self.all_src = dg.new_of.contiguous()      # every node, original order -> degree-order id (cols mode)
         self.rows = torch.arange(rank, n, world, dtype=torch.int32, device=dev)
         self.n_src = int(self.rows.numel())
         self.src = dg.new_of[self.rows.long()].contiguous()
@@ -190,6 +203,14 @@ class ShardedDegreeHSD:
         gathered table."""
         from ._lib import check, lib
         dg = self.dg
+        if self.ring_mode == "cols":
+            import torch.distributed as dist
+            self._counts = engine.ring_counts_cols(dg, self.hops, self.rank, self.world,
+                                                   getattr(self, "_counts", None))
+            dist.all_reduce(self._counts, op=dist.ReduceOp.SUM, group=self.group)
+            engine.signature_from_counts(dg, self.hops, self._counts, self.all_src, self.table_row, self.sig_all,
+                                         self.sizes, self.empty, self.status)
+            return
         if self.n_src == 0:
             return
         engine.ensure_bfs_workspace(dg.n, dg.rowptr.device)
@@ -232,8 +253,8 @@ class ShardedDegreeHSD:
     def gather(self) -> None:
         """Make every rank's signature table complete: a barrier in peer mode (the rows were
         already stored by the BFS kernels), else the in-place NCCL all-gather."""
-        if self.world == 1:
-            return
+        if self.world == 1 or self.ring_mode == "cols":
+            return      # cols: the all-reduce left the complete table on every rank
         if self.sig_peer_ptrs is not None:
             # the rows were already stored into every rank's table by the BFS kernel: only wait
             if self.sig_symm is not None:

@@ -114,6 +114,24 @@ int hsd_ring_signature_degree_dense(const int32_t* rowptr, const int32_t* col, i
                                     int32_t* status, uint32_t* workspace, int64_t workspace_words, int64_t nnz,
                                     void* stream);
 
+/* Dense variant across several GPUs, split by bitmap COLUMNS: the OR recursion is independent per bitmap word,
+ * so rank r runs every level for ALL nodes on its own range of 16-byte bitmap pieces [word4_begin, word4_end)
+ * with no exchange (1/W of the work and of the table memory) and emits the PARTIAL integer prefix counts of
+ * that range: counts[s][(h-1)(n_bins-1) + b] = members of ring_h(s) in the range with id < bin_end[b],
+ * counts[s][hops (n_bins-1) + h-1] = members of ring_h(s) in the range (s = degree-order id; ld_c >=
+ * hops (n_bins-1) + hops).  The caller sums `counts` over the ranks (one integer all-reduce: exact and
+ * order-free) and hsd_ring_signature_from_counts turns the sums into the same signature rows / ring sizes /
+ * status as the other variants, bit for bit.  workspace: hsd_ring_cols_workspace_words(...) uint32 words. */
+int64_t hsd_ring_cols_workspace_words(int32_t n_nodes, int32_t word4_begin, int32_t word4_end);
+int hsd_ring_counts_dense_cols(const int32_t* rowptr, const int32_t* col, int32_t n_nodes, int64_t nnz,
+                               int32_t hops, const int32_t* bin_end, int32_t n_bins,
+                               int32_t word4_begin, int32_t word4_end, int32_t* counts, int64_t ld_c,
+                               uint32_t* workspace, int64_t workspace_words, void* stream);
+int hsd_ring_signature_from_counts(const int32_t* rowptr, const int32_t* counts, int64_t ld_c,
+                                   const int32_t* src_nodes, const int32_t* out_rows, int32_t n_src,
+                                   int32_t hops, const float* delta, int32_t n_bins, float* sig, int64_t sig_ld,
+                                   int32_t* ring_sizes, int32_t empty_as_zero, int32_t* status, void* stream);
+
 /* Graphs above ~400k nodes: the four N-bit bitmaps of a source no longer fit shared memory.  The
  * BFS entry points then use a caller-owned DEVICE workspace of hsd_bfs_workspace_words(n_nodes)
  * uint32 words (0 = not needed), registered per host thread with hsd_bfs_set_workspace (NULL

@@ -127,3 +127,39 @@ def test_multihsd_column_shards_compose_the_embedding(golden_graphs):
     assert torch.allclose(acc, full, rtol=1e-12, atol=1e-15)
     single = m.embed_device_sharded(0, 1)
     assert torch.equal(single, full)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+@pytest.mark.parametrize("n,hops", [(2500, 3), (4100, 2), (900, 4)])
+def test_column_split_dense_ring_variant(world, n, hops):
+    """hsd_ring_counts_dense_cols + hsd_ring_signature_from_counts: every emulated rank runs the bitmap
+    recursion for all nodes on its own 1/world of the bitmap columns; the partial integer counts summed
+    over the ranks (what the all-reduce does) give signatures, ring sizes and the empty-ring flag
+    bit-identical to the single-GPU kernels — with isolated nodes and both empty-ring policies."""
+    import torch
+    from hsd_b200 import engine
+    from hsd_b200.graph import CSRGraph, powerlaw_graph
+    g0 = powerlaw_graph(n, 4, seed=world)
+    rows = np.repeat(np.arange(g0.n), np.diff(g0.rowptr))
+    e = np.stack([rows, g0.col], 1)
+    g = CSRGraph.from_edges(n + 2, e[rows < g0.col])              # two isolated nodes
+    dg = engine.DeviceGraph.upload(g, include_zero=True)
+    ref_sig, ref_sizes, _, ref_status = engine.ring_signature_degree(dg, hops, empty="zero")
+    total = None
+    for r in range(world):
+        c = engine.ring_counts_cols(dg, hops, r, world).clone()
+        total = c if total is None else total + c
+    src = dg.new_of.contiguous()
+    out_rows = torch.arange(g.n, dtype=torch.int32, device="cuda")
+    for empty in ("zero", "raise"):
+        sig = torch.zeros_like(ref_sig)
+        sizes = torch.zeros_like(ref_sizes)
+        status = torch.zeros(1, dtype=torch.int32, device="cuda")
+        engine.signature_from_counts(dg, hops, total, src, out_rows, sig, sizes, empty, status)
+        torch.cuda.synchronize()
+        assert torch.equal(sizes, ref_sizes)
+        if empty == "zero":
+            assert torch.equal(sig, ref_sig) and int(status.item()) == 0
+        else:
+            assert int(status.item()) & 1                         # the isolated nodes' rings are empty
+    assert engine.ring_cols_range(g.n, world - 1, world)[1] == ((g.n + 31) // 32 + 3) // 4

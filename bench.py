@@ -313,6 +313,8 @@ def measure_degree_path(ctx, g, hops, steps, warmup, workload_key):
     pairs = n * (n - 1) / 2
 
     def one_step(ev=None):
+        if ev is not None:
+            ev[4].record()
         ctx.flush.fill_(1.0)               # evict the previous step's tables from L2
         if ev is not None:
             ev[0].record()
@@ -321,7 +323,8 @@ def measure_degree_path(ctx, g, hops, steps, warmup, workload_key):
             ev[1].record()
         plan.gather()
         if ev is not None:
-            plan.distances(ev[2], ev[3])
+            plan.distances(ev[2], ev[3])   # (N > 1: ends with the device-side barrier that completes the blocks)
+            ev[5].record()
         else:
             plan.distances()
 
@@ -330,7 +333,7 @@ def measure_degree_path(ctx, g, hops, steps, warmup, workload_key):
     torch.cuda.synchronize()
     plan.check()
 
-    events = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(steps)]
+    events = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(steps)]
     sampler = ClockSampler(ctx.local_rank)
     ctx.barrier()
     torch.cuda.synchronize()
@@ -348,6 +351,8 @@ def measure_degree_path(ctx, g, hops, steps, warmup, workload_key):
     bfs_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in events]))
     gather_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in events]))
     pair_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in events]))
+    flush_ms = float(np.mean([e[4].elapsed_time(e[0]) for e in events]))
+    tail_ms = float(np.mean([e[3].elapsed_time(e[5]) for e in events]))
 
     # ---- roofline of the dominant kernel (pairwise L1) ----
     # algorithmic flops per launch = 2 (subtract, |.|-accumulate) x unordered pairs this launch
@@ -427,7 +432,8 @@ def measure_degree_path(ctx, g, hops, steps, warmup, workload_key):
         "note": ring_note,
     }
     rec = {"ms_per_step": ms_per_step, "value": value, "pairs": pairs, "peer": peer, "k_alg": k_alg,
-           "n_bins": dg.n_bins, "stage_ms": {"bfs_signature": bfs_ms, "allgather_transpose": gather_ms, "pairwise": pair_ms},
+           "n_bins": dg.n_bins, "stage_ms": {"l2_flush": flush_ms, "bfs_signature": bfs_ms, "allgather_transpose": gather_ms, "pairwise": pair_ms,
+                        "final_barrier": tail_ms},
            "roofline": roofline, "roofline_bfs": roofline_bfs, "clocks": clocks,
            # ring phase: scatter + hops CDF passes + (hops - 1) OR passes (dense, unfused; the fused build for 32k < N <= 131k
            # launches hops + 2), or one BFS kernel (two with the hub split); then transpose + pairwise

@@ -354,6 +354,14 @@ def measure_degree_path(ctx, g, hops, steps, warmup, workload_key):
     flush_ms = float(np.mean([e[4].elapsed_time(e[0]) for e in events]))
     tail_ms = float(np.mean([e[3].elapsed_time(e[5]) for e in events]))
 
+    per_rank = None
+    if world > 1:   # the same stage times on every rank (rank skew shows up as waiting at the barriers)
+        mine = torch.tensor([bfs_ms, gather_ms, pair_ms, tail_ms], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        ctx.dist.all_gather(allr, mine)
+        per_rank = {k: [round(float(t[i]), 4) for t in allr]
+                    for i, k in enumerate(("bfs_signature", "allgather_transpose", "pairwise", "final_barrier"))}
+
     # ---- roofline of the dominant kernel (pairwise L1) ----
     # algorithmic flops per launch = 2 (subtract, |.|-accumulate) x unordered pairs this launch
     # covers x signature length; hop 0 is one scalar (the kernel treats it so), every later hop B-1 gaps
@@ -434,6 +442,7 @@ def measure_degree_path(ctx, g, hops, steps, warmup, workload_key):
     rec = {"ms_per_step": ms_per_step, "value": value, "pairs": pairs, "peer": peer, "k_alg": k_alg,
            "n_bins": dg.n_bins, "stage_ms": {"l2_flush": flush_ms, "bfs_signature": bfs_ms, "allgather_transpose": gather_ms, "pairwise": pair_ms,
                         "final_barrier": tail_ms},
+           "stage_ms_per_rank": per_rank,
            "roofline": roofline, "roofline_bfs": roofline_bfs, "clocks": clocks,
            # ring phase: scatter + hops CDF passes + (hops - 1) OR passes (dense, unfused; the fused build for 32k < N <= 131k
            # launches hops + 2), or one BFS kernel (two with the hub split); then transpose + pairwise
@@ -711,7 +720,7 @@ def run_native(args):
                 r3, p3, d3 = measure_degree_path(ctx, g3, 4, 3, 1, "c3")
                 extras["north_star_c3"] = {
                     "config": workload_config(100000, 4, world, r3["peer"], r3["n_bins"]), "n_gpus": world, "steps": 3, "warmup": 1,
-                    "ms_per_step": r3["ms_per_step"], "value": r3["value"], "unit": UNIT, "stage_ms": r3["stage_ms"],
+                    "ms_per_step": r3["ms_per_step"], "value": r3["value"], "unit": UNIT, "stage_ms": r3["stage_ms"], "stage_ms_per_rank": r3["stage_ms_per_rank"],
                     "frac": r3["roofline"]["frac"], "roofline": r3["roofline"], "roofline_bfs": r3["roofline_bfs"],
                     "clocks": r3["clocks"]}
                 del p3, d3, g3
@@ -745,7 +754,7 @@ def run_native(args):
             "warmup": args.warmup, "ms_per_step": rec["ms_per_step"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(n, hops, world, peer, rec["n_bins"]),
-            "stage_ms": rec["stage_ms"],
+            "stage_ms": rec["stage_ms"], "stage_ms_per_rank": rec["stage_ms_per_rank"],
             "roofline": rec["roofline"], "roofline_bfs": rec["roofline_bfs"], "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(args.steps * rec["launches_per_step"]),
             "clocks": rec["clocks"],

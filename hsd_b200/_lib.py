@@ -15,7 +15,7 @@ from .build import LIB
 HEADER_SYMBOLS = [
     "hsd_version", "hsd_last_error_string", "hsd_ring_signature_degree", "hsd_ring_signature_degree_allgather", "hsd_bfs_rings",
     "hsd_bfs_workspace_words", "hsd_bfs_set_workspace",
-    "hsd_signature_transpose", "hsd_scatter_symmetric", "hsd_pairwise_l1", "hsd_pairwise_l1_sharded", "hsd_ring_signature_values",
+    "hsd_signature_transpose", "hsd_scatter_symmetric", "hsd_pairwise_l1", "hsd_pairwise_l1_sharded", "hsd_pairwise_l1_tile_list", "hsd_ring_signature_values",
     "hsd_pairwise_w1_merge", "hsd_pairwise_aligned", "hsd_pairwise_worker", "hsd_cheb_spmm", "hsd_laplacian_spmv", "hsd_ring_reduce", "hsd_characteristic_function", "hsd_topk_rows",
     "hsd_fp32_peak_probe", "hsd_copy2d_to_host", "hsd_mirror_upper_to_lower_host", "hsd_exact_wavelets", "hsd_ring_dense_workspace_words", "hsd_ring_signature_degree_dense",
     "hsd_ring_cols_workspace_words", "hsd_ring_counts_dense_cols", "hsd_ring_signature_from_counts",
@@ -63,6 +63,7 @@ lib.hsd_scatter_symmetric.argtypes = [_P, c_int64, c_int32, c_int32, _P, _P, c_i
 lib.hsd_pairwise_l1.argtypes = [_P, c_int32, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32,
                                 _P, c_int64, _P]
 lib.hsd_pairwise_l1_sharded.argtypes = [_P, c_int32, c_int64, c_int32, c_int32, c_int32, c_int32, _P, c_int64, _P]
+lib.hsd_pairwise_l1_tile_list.argtypes = [_P, c_int32, c_int64, c_int32, _P, c_int32, c_int32, c_int32, _P, c_int64, _P]
 lib.hsd_ring_signature_values.argtypes = [_P, c_int64, _P, _P, _P, _P, c_int32, c_int32, c_int32,
                                           c_int32, _P, _P]
 lib.hsd_pairwise_w1_merge.argtypes = [_P, _P, _P, c_int32, c_int32, c_int32, c_int32, c_int32,

@@ -14,7 +14,9 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libhsd_b200.so")
+# HSD_B200_LIB: load / build an alternative library file (kernel-variant experiments: a second build with
+# other -D flags next to the shipped one); HSD_B200_NVCC_FLAGS: extra nvcc flags for that build
+LIB = os.environ.get("HSD_B200_LIB") or os.path.join(HERE, "libhsd_b200.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -51,13 +53,14 @@ def needs_build() -> bool:
 def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" if not os.environ.get("HSD_B200_LIB") else
+                          "build_" + os.path.basename(LIB).replace(".", "_"))
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []
     for src in sources():
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
-        cmd = [_nvcc(), *NVCC_FLAGS, "-c", src, "-o", obj]
+        cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("HSD_B200_NVCC_FLAGS", "").split(), "-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     gxx = shutil.which("g++") or "g++"

@@ -26,6 +26,9 @@ constexpr int KC = HSD_PAIR_KCHUNK;
 constexpr int STAGES = 4;
 constexpr int LOOKAHEAD = 2;   // chunks in flight ahead of the one being consumed
 constexpr int PAIR_THREADS = 256;
+#ifndef HSD_PAIR_LANE_MAP
+#define HSD_PAIR_LANE_MAP 0
+#endif
 #ifndef HSD_PAIR_V2_DEFAULT
 #define HSD_PAIR_V2_DEFAULT 32, 3, 1, 0, 2, 8   // kc (0 = round-1 kernel), stages, packed, (unused), lookahead, unroll
 #endif
@@ -109,8 +112,35 @@ struct PairArgs {
     // v2 (persistent) kernel: tiles of this launch, valid rows of the last K chunk rounded up to 4,
     // chunks the elected producer thread runs ahead when there is no producer warp
     int n_tiles, k_last, lookahead;
+    // explicit tile list (sharded runs): entry t = {first row, first column, mirror flag}; nullptr: tiles are
+    // enumerated from the launch rectangle / triangle
+    const int32_t* tile_list;
+    int list_tile_n;              // 128 or 64: column width of the listed tiles
     unsigned int* tile_counter;   // dynamic tile scheduler: zeroed before the launch
 };
+
+// Thread -> (tx, ty) position in the 16 x 16 thread grid of a tile (thread (tx, ty) owns columns tx*4.. and
+// rows ty*4.. of each 64-wide half).  The map decides which lanes of a warp sit side by side, i.e. how long the
+// contiguous runs of a warp's result stores are — which matters when the stores cross NVLink (peer-mapped blocks):
+//   0: warp = 16 tx x 2 ty  -> direct stores 2 rows x 256 B, mirrored stores 16 rows x 32 B   (round 1)
+//   1: warp =  4 tx x 8 ty  -> direct 8 rows x 64 B,  mirrored 4 rows x 128 B
+//   2: warp =  8 tx x 4 ty  -> direct 4 rows x 128 B, mirrored 8 rows x 64 B
+// Operand reads stay conflict-free broadcasts in every map (a warp reads 8/4/2 distinct 16-byte pieces of A
+// and 4/8/16 of B per LDS.128).
+__device__ __forceinline__ void tile_thread_pos(int tid, int& tx, int& ty) {
+    constexpr int lane_map = HSD_PAIR_LANE_MAP;      // compile-time: a run-time choice costs the v2 kernel registers (spills)
+    const int lane = tid & 31, w = tid >> 5;
+    if (lane_map == 1) {
+        tx = (w & 3) * 4 + (lane & 3);
+        ty = (w >> 2) * 8 + (lane >> 2);
+    } else if (lane_map == 2) {
+        tx = (w & 1) * 8 + (lane & 7);
+        ty = (w >> 1) * 4 + (lane >> 3);
+    } else {
+        tx = tid & 15;
+        ty = tid >> 4;
+    }
+}
 
 // pointer to logical element (i, 0)
 __device__ __forceinline__ float* row_ptr(const PairArgs& p, int i) {
@@ -194,7 +224,8 @@ pairwise_l1_kernel(const __grid_constant__ CUtensorMap tmap, const PairArgs p) {
         for (int n = 0; n < LOOKAHEAD && n < p.k_chunks; ++n) issue_chunk(n);
 
     // ===== 16 x 16 threads, each 8 x 8 outputs (2 x 2 blocks of 4 x 4) =====
-    const int tx = tid & 15, ty = tid >> 4;
+    int tx, ty;
+    tile_thread_pos(tid, tx, ty);
     float acc[8][8];
 #pragma unroll
     for (int r = 0; r < 8; ++r)
@@ -329,15 +360,25 @@ pairwise_l1_n64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     extern __shared__ __align__(128) unsigned char pair_smem_raw[];
     PairSmemN64& sm = *reinterpret_cast<PairSmemN64*>(pair_smem_raw);
 
-    int I, J;
-    if (p.symmetric) {
-        tri_decode_n64(blockIdx.x * p.tile_stride + p.tile_offset, p.tiles_r, p.tiles_c, I, J);
+    int i_base, j_base;
+    bool mirror;
+    if (p.tile_list) {
+        const int32_t* e = p.tile_list + 3 * (int64_t)blockIdx.x;
+        i_base = __ldg(e);
+        j_base = __ldg(e + 1);
+        mirror = __ldg(e + 2) != 0;
     } else {
-        I = blockIdx.x / p.tiles_c;
-        J = blockIdx.x - I * p.tiles_c;
+        int I, J;
+        if (p.symmetric) {
+            tri_decode_n64(blockIdx.x * p.tile_stride + p.tile_offset, p.tiles_r, p.tiles_c, I, J);
+        } else {
+            I = blockIdx.x / p.tiles_c;
+            J = blockIdx.x - I * p.tiles_c;
+        }
+        i_base = p.row0 + I * TILE;
+        j_base = p.col0 + J * TILE_N64;
+        mirror = p.symmetric && (J >= 2 * I + 2);
     }
-    const int i_base = p.row0 + I * TILE;
-    const int j_base = p.col0 + J * TILE_N64;
 
     const int tid = threadIdx.x;
     if (tid == 0) {
@@ -362,7 +403,8 @@ pairwise_l1_n64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     if (tid == 0)
         for (int n = 0; n < LOOKAHEAD && n < p.k_chunks; ++n) issue_chunk(n);
 
-    const int tx = tid & 15, ty = tid >> 4;
+    int tx, ty;
+    tile_thread_pos(tid, tx, ty);
     float acc[8][4];
 #pragma unroll
     for (int r = 0; r < 8; ++r)
@@ -399,7 +441,6 @@ pairwise_l1_n64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     }
 
     const int row_end = p.row0 + p.n_rows, col_end = p.col0 + p.n_cols;
-    const bool mirror = p.symmetric && (J >= 2 * I + 2);
     const bool full_tile = (i_base + TILE <= row_end) && (j_base + TILE_N64 <= col_end) && p.vec_ok;
     if (full_tile) {
 #pragma unroll
@@ -529,13 +570,24 @@ pairwise_l1_v2_kernel(const __grid_constant__ CUtensorMap tmap, const PairArgs p
     __syncthreads();
 
     const int k_chunks = p.k_chunks;
-    auto tile_origin = [&](int t, int& I, int& J) {
+    auto tile_origin = [&](int t, int& i_base, int& j_base, bool& mirror) {
+        if (p.tile_list) {
+            const int32_t* e = p.tile_list + 3 * (int64_t)t;
+            i_base = __ldg(e);
+            j_base = __ldg(e + 1);
+            mirror = __ldg(e + 2) != 0;
+            return;
+        }
+        int I, J;
         if (p.symmetric) {
             tri_decode(t * p.tile_stride + p.tile_offset, p.tiles_r, p.tiles_c, I, J);
         } else {
             I = t / p.tiles_c;
             J = t - I * p.tiles_c;
         }
+        i_base = p.row0 + I * TILE;
+        j_base = p.col0 + J * TILE;
+        mirror = p.symmetric && I != J;
     };
 
     // ---- producer cursor: (tile, chunk), one stage per chunk.  Tiles come from a global counter
@@ -559,10 +611,8 @@ pairwise_l1_v2_kernel(const __grid_constant__ CUtensorMap tmap, const PairArgs p
                 return;
             }
             sm.tile_of_stage[ps] = pt;
-            int I, J;
-            tile_origin(pt, I, J);
-            pi_base = p.row0 + I * TILE;
-            pj_base = p.col0 + J * TILE;
+            bool unused;
+            tile_origin(pt, pi_base, pj_base, unused);
         }
         mbar_expect_tx(full, BYTES);
         tma_load_2d(smem_u32(&sm.a[ps][0][0]), &tmap, pi_base, pc * KC_, full);
@@ -575,7 +625,8 @@ pairwise_l1_v2_kernel(const __grid_constant__ CUtensorMap tmap, const PairArgs p
         for (int n = 0; n < p.lookahead; ++n) produce_one();
 
     // ===== consumers: 16 x 16 threads, each 8 x 8 outputs (2 x 2 blocks of 4 x 4) =====
-    const int tx = tid & 15, ty = tid >> 4;
+    int tx, ty;
+    tile_thread_pos(tid, tx, ty);
     float acc[8][8];
 #pragma unroll
     for (int r = 0; r < 8; ++r)
@@ -624,9 +675,9 @@ pairwise_l1_v2_kernel(const __grid_constant__ CUtensorMap tmap, const PairArgs p
         }
 
         // ---- epilogue: direct store (+ mirrored store for off-diagonal symmetric tiles) ----
-        int I, J;
-        tile_origin(t, I, J);
-        const int i_base = p.row0 + I * TILE, j_base = p.col0 + J * TILE;
+        int i_base, j_base;
+        bool mirror;
+        tile_origin(t, i_base, j_base, mirror);
         const bool full_tile = (i_base + TILE <= row_end) && (j_base + TILE <= col_end) && p.vec_ok &&
                                (!p.shard_ptrs || p.per >= TILE);
         if (full_tile) {
@@ -638,7 +689,7 @@ pairwise_l1_v2_kernel(const __grid_constant__ CUtensorMap tmap, const PairArgs p
                 *reinterpret_cast<float4*>(o + tx * 4) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
                 *reinterpret_cast<float4*>(o + 64 + tx * 4) = make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]);
             }
-            if (p.symmetric && I != J) {
+            if (mirror) {
                 const TileRows rj = tile_rows(p, j_base);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
@@ -658,7 +709,7 @@ pairwise_l1_v2_kernel(const __grid_constant__ CUtensorMap tmap, const PairArgs p
                     const int j = j_base + (q < 4 ? tx * 4 + q : 64 + tx * 4 + (q - 4));
                     if (j >= col_end) continue;
                     row_ptr(p, i)[j] = acc[r][q];
-                    if (p.symmetric && I != J) row_ptr(p, j)[i] = acc[r][q];
+                    if (mirror) row_ptr(p, j)[i] = acc[r][q];
                 }
             }
         }
@@ -841,7 +892,8 @@ static int launch_pairwise(const float* sigT, int32_t k_used, int64_t n_pad, Pai
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const bool use_n64 = tile_n == 64 || (tile_n == 0 && n_tiles < (long long)sms * 2 * 8);
+    bool use_n64 = tile_n == 64 || (tile_n == 0 && n_tiles < (long long)sms * 2 * 8);
+    if (a.tile_list) use_n64 = (a.list_tile_n == 64);     // an explicit tile list fixes the tile shape
     if (!use_n64) {
         // large launches: persistent, dynamically scheduled 128 x 128 kernel (v2); the 128 x 64 kernel
         // below keeps the small launches (few tiles per CTA slot: its finer tiles quantise better)
@@ -853,7 +905,8 @@ static int launch_pairwise(const float* sigT, int32_t k_used, int64_t n_pad, Pai
         const int tr = a.tiles_r;
         const int tc = (a.n_cols + TILE_N64 - 1) / TILE_N64;
         const long long total = a.symmetric ? (long long)tr * tc - (long long)tr * (tr - 1) : (long long)tr * tc;
-        const long long mine = total > a.tile_offset ? (total - a.tile_offset + a.tile_stride - 1) / a.tile_stride : 0;
+        const long long mine = a.tile_list ? n_tiles
+                               : (total > a.tile_offset ? (total - a.tile_offset + a.tile_stride - 1) / a.tile_stride : 0);
         if (mine <= 0) return HSD_OK;
         HSD_REQUIRE(mine < (1ll << 31), "too many tiles for one launch");
         a.tiles_c = tc;
@@ -873,6 +926,10 @@ static int launch_pairwise(const float* sigT, int32_t k_used, int64_t n_pad, Pai
         return HSD_OK;
     }
 
+    if (a.tile_list) {
+        set_error("explicit tile lists need the v2 kernel (HSD_PAIR_V2 must not be 0)");
+        return HSD_ERR_UNSUPPORTED;
+    }
     const int smem = (int)sizeof(PairSmem);
     static int unroll = 0;   // tuning knob, read once: HSD_PAIR_UNROLL in {4, 8, 16}
     if (!unroll) {
@@ -959,4 +1016,28 @@ extern "C" int hsd_fp32_peak_probe(float* sink, int32_t iters, int64_t* lane_ops
     // 64 sub + 64 |.|-accumulate + 16 operand updates = 144 FADD per thread-iteration
     if (lane_ops_host) *lane_ops_host = (int64_t)blocks * 256 * (int64_t)iters * (128 + 16);
     return HSD_OK;
+}
+
+extern "C" int hsd_pairwise_l1_tile_list(const float* sigT, int32_t k_used, int64_t n_pad, int32_t n_nodes,
+                                         const int32_t* tile_list, int32_t n_tiles, int32_t tile_n,
+                                         int32_t rows_per_rank, float* const* shard_ptrs, int64_t ld_out,
+                                         void* stream) {
+    using namespace hsd;
+    HSD_REQUIRE(sigT && shard_ptrs && (tile_list || n_tiles == 0), "null pointer");
+    HSD_REQUIRE(k_used > 0, "k_used must be positive");
+    HSD_REQUIRE(n_pad > 0 && n_pad % 4 == 0 && n_nodes > 0 && n_nodes <= n_pad, "bad n_pad / n_nodes");
+    HSD_REQUIRE((reinterpret_cast<uintptr_t>(sigT) & 15) == 0, "sigT must be 16-byte aligned");
+    HSD_REQUIRE(tile_n == 128 || tile_n == 64, "tile_n must be 128 or 64");
+    HSD_REQUIRE(rows_per_rank > 0 && n_tiles >= 0, "bad sizes");
+    HSD_REQUIRE(ld_out >= n_nodes && ld_out % 4 == 0, "ld_out must be >= n_nodes and a multiple of 4");
+    if (n_tiles == 0) return HSD_OK;
+    PairArgs a = {};
+    a.row0 = 0; a.n_rows = n_nodes; a.col0 = 0; a.n_cols = n_nodes;
+    a.tiles_r = a.tiles_c = (n_nodes + TILE - 1) / TILE;
+    a.symmetric = 1;
+    a.out = nullptr; a.ld = ld_out;
+    a.vec_ok = 1;
+    a.shard_ptrs = shard_ptrs; a.per = rows_per_rank; a.tile_stride = 1; a.tile_offset = 0;
+    a.tile_list = tile_list; a.list_tile_n = tile_n;
+    return launch_pairwise(sigT, k_used, n_pad, a, n_tiles, (cudaStream_t)stream);
 }

@@ -68,6 +68,63 @@ def agree_status(status: torch.Tensor, world: int, group=None) -> int:
     return int(status.reshape(-1)[0].item())
 
 
+def symmetric_tile_list(n: int, world: int, per: int, rank: int, tile_n: int = 128):
+    """Rank `rank`'s share of the upper-triangle 128 x 128 tiles of the N x N matrix, as int32[m, 3] rows
+    {first row, first column, mirror flag} of 128 x tile_n tiles (tile_n = 64 splits every tile in two).
+
+    Every tile {I, J} is computed by the owner of row block I or of row block J (checkerboard on I + J, then
+    a rebalancing pass that moves tiles between their two possible owners until every rank has the same
+    count), and is ORIENTED so that its mirrored store — the short-run one — lands in the computing rank's
+    own block and only the direct store (256-byte runs) crosses NVLink.  Against round-robin dealing
+    (hsd_pairwise_l1_sharded) that halves the peer traffic and removes every 32-byte remote write.
+    Deterministic: every rank derives the same global assignment."""
+    import numpy as np
+    T = (n + 127) // 128
+    I, J = np.triu_indices(T)
+    own = lambda t: np.minimum(t * 128 // per, world - 1)
+    oI, oJ = own(I), own(J)
+    comp = np.where(((I + J) & 1) == 0, oI, oJ)
+    cnt = np.bincount(comp, minlength=world).astype(np.int64)
+    target = -(-len(I) // world)
+    for _ in range(10 * world):                 # move tiles from the fullest rank to their other possible owner
+        hi = int(cnt.argmax())
+        if cnt[hi] <= target:
+            break
+        cand = np.nonzero((comp == hi) & (oI != oJ))[0]
+        other = np.where(oI[cand] == hi, oJ[cand], oI[cand])
+        moved = False
+        for r in np.argsort(cnt, kind="stable"):
+            if cnt[r] >= target or r == hi:
+                continue
+            c = cand[other == r]
+            k = int(min(len(c), cnt[hi] - target, target - cnt[r]))
+            if k > 0:
+                comp[c[:k]] = r
+                cnt[hi] -= k
+                cnt[r] += k
+                moved = True
+                break
+        if not moved:
+            break
+    mine = comp == rank
+    I, J, by_row_owner = I[mine], J[mine], (comp == oI)[mine]
+    # rows of the listed tile = the REMOTE block (direct store), columns = the local block (mirrored store)
+    X = np.where(by_row_owner, J, I)
+    Y = np.where(by_row_owner, I, J)
+    order = np.lexsort((Y, X))                 # consecutive tiles share their A rows (L2)
+    X, Y = X[order], Y[order]
+    mirror = (X != Y).astype(np.int64)
+    if tile_n == 128:
+        out = np.stack([X * 128, Y * 128, mirror], 1)
+    else:
+        lo = np.stack([X * 128, Y * 128, mirror], 1)
+        hi_half = np.stack([X * 128, Y * 128 + 64, mirror], 1)
+        hi_half = hi_half[hi_half[:, 1] < n]
+        out = np.concatenate([lo, hi_half])
+        out = out[np.lexsort((out[:, 1], out[:, 0]))]
+    return torch.from_numpy(np.ascontiguousarray(out.astype(np.int32)))
+
+
 class ShardedDegreeHSD:
     """Plan + buffers for repeated evaluation of one graph on `world` ranks."""
 
@@ -161,6 +218,14 @@ class ShardedDegreeHSD:
                 self.out_full = symm_mem.empty((self.per, self.ld_out), dtype=torch.float32, device=dev)
                 self.symm = symm_mem.rendezvous(self.out_full, group if group is not None else dist.group.WORLD)
             self.ptrs = torch.tensor([int(p) for p in self.symm.buffer_ptrs], dtype=torch.int64, device=dev)
+        self.tile_list = None
+        if self.peer and os.environ.get("HSD_PAIR_SHARD_TILES", "owner") == "owner":
+            # tiles dealt to the owners of their row / column blocks, mirrored store local (symmetric_tile_list);
+            # 128 x 64 tiles when a rank has few tiles per CTA slot, like the single-GPU dispatch
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            t128 = ((n + 127) // 128) * ((n + 127) // 128 + 1) // 2 // world
+            self.tile_n = 64 if t128 < sms * 2 * 8 else 128
+            self.tile_list = symmetric_tile_list(n, world, self.per, rank, self.tile_n).to(dev)
         if self.peer:
             self.out = self.out_full[:max(self.n_rows, 1), :n]
         else:
@@ -282,9 +347,15 @@ class ShardedDegreeHSD:
             ev_before.record()
         if self.peer:
             from ._lib import check, lib
-            check(lib.hsd_pairwise_l1_sharded(engine._ptr(self.sigT), self.k_used, self.sigT.stride(0),
-                                              n, self.rank, self.world, self.per, engine._ptr(self.ptrs),
-                                              self.ld_out, engine._stream()))
+            if self.tile_list is not None:
+                check(lib.hsd_pairwise_l1_tile_list(engine._ptr(self.sigT), self.k_used, self.sigT.stride(0), n,
+                                                    engine._ptr(self.tile_list), int(self.tile_list.shape[0]),
+                                                    self.tile_n, self.per, engine._ptr(self.ptrs), self.ld_out,
+                                                    engine._stream()))
+            else:
+                check(lib.hsd_pairwise_l1_sharded(engine._ptr(self.sigT), self.k_used, self.sigT.stride(0),
+                                                  n, self.rank, self.world, self.per, engine._ptr(self.ptrs),
+                                                  self.ld_out, engine._stream()))
             return self.out[:self.n_rows]
         if self.n_rows == 0:
             return self.out[:0]

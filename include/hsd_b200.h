@@ -197,6 +197,17 @@ int hsd_pairwise_l1_sharded(const float* sigT, int32_t k_used, int64_t n_pad, in
                             int32_t rank, int32_t world, int32_t rows_per_rank,
                             float* const* shard_ptrs, int64_t ld_out, void* stream);
 
+/* The same kernels driven by an explicit tile list (round 2): tile_list int32[n_tiles][3] = {first row, first
+ * column, mirror flag} of 128 x tile_n tiles (tile_n = 128 or 64; rows / columns are node ids, multiples of
+ * 128 / tile_n).  A listed tile is stored to the owner of its rows and, when the flag is set, mirrored to the
+ * owner of its columns.  The host deals the upper-triangle tiles so that every tile is computed by the owner
+ * of its ROW block or of its COLUMN block, oriented so that the mirrored (short-run) store is the local one
+ * and only the direct (long-run) store crosses NVLink: half the peer traffic of hsd_pairwise_l1_sharded's
+ * round-robin dealing, none of it in 32-byte pieces (hsd_b200/sharded.py::symmetric_tile_list). */
+int hsd_pairwise_l1_tile_list(const float* sigT, int32_t k_used, int64_t n_pad, int32_t n_nodes,
+                              const int32_t* tile_list, int32_t n_tiles, int32_t tile_n,
+                              int32_t rows_per_rank, float* const* shard_ptrs, int64_t ld_out, void* stream);
+
 /* ---- K2 (value mode): ring gather + sort ----------------------------------
  * Replaces model/HSD.py:71-83 (get_hierarchical_coeffcients) plus the argsort
  * inside scipy's _cdf_distance.  For each (row r, hop h) gathers

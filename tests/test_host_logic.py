@@ -325,3 +325,33 @@ def test_host_mirror_completes_the_symmetric_matrix(n, panels, threads):
         check(lib.hsd_mirror_upper_to_lower_host(D.ctypes.data, n, n, p0, p0 + pr, threads))
     assert np.array_equal(D, U + np.triu(U, 1).T)
     assert lib.hsd_mirror_upper_to_lower_host(D.ctypes.data, n, n, 5, 64, 1) == -1     # panels start on 64-row boundaries
+
+
+@pytest.mark.parametrize("n,world", [(20000, 8), (2500, 3), (1801, 4), (300, 2), (100000, 8)])
+@pytest.mark.parametrize("tile_n", [128, 64])
+def test_symmetric_tile_list_covers_every_tile_once(n, world, tile_n):
+    """sharded.symmetric_tile_list: over the ranks every upper-triangle tile appears exactly once, is computed
+    by the owner of its row block or of its column block, is oriented so that the mirrored store is local,
+    and the ranks' shares are balanced."""
+    from hsd_b200.sharded import shard_rows, symmetric_tile_list
+    per = shard_rows(n, world, 0)[2]
+    own = lambda t: min(t * 128 // per, world - 1)
+    seen, halves_of, counts = set(), {}, []
+    for r in range(world):
+        tl = symmetric_tile_list(n, world, per, r, tile_n).numpy()
+        counts.append(len(tl))
+        for i0, j0, m in tl.tolist():
+            assert i0 % 128 == 0 and j0 % tile_n == 0 and i0 < n and j0 < n
+            key = (min(i0 // 128, j0 // 128), max(i0 // 128, j0 // 128), (j0 % 128) // 64)
+            assert key not in seen
+            seen.add(key)
+            halves_of.setdefault(key[:2], (j0 // 128, set()))[1].add(key[2])
+            assert (m == 1) == (i0 // 128 != j0 // 128)
+            assert own(j0 // 128) == r          # the mirrored store (rows of the column block) is local ...
+            assert m == 1 or own(i0 // 128) == r   # ... and a diagonal tile is entirely local
+    T = (n + 127) // 128
+    assert len(halves_of) == T * (T + 1) // 2                       # every unordered pair of 128-blocks, once
+    for (a, b), (y, halves) in halves_of.items():                   # with every existing half of its column block
+        want = {0} if tile_n == 128 else {h for h in (0, 1) if y * 128 + 64 * h < n}
+        assert halves == want
+    assert max(counts) <= -(-sum(counts) // world) * 1.03 + 2           # nobody is overloaded (some halves do not exist)

@@ -383,8 +383,10 @@ def measure_degree_path(ctx, g, hops, steps, warmup, workload_key):
     except Exception:
         pass
     fp32_peak = ctx.fp32_peak
+    pair_kernel = ("pairwise_l1_n64_kernel (128 x 64 tiles, one per CTA)" if getattr(plan, "tile_list", None) is not None
+                   and getattr(plan, "tile_n", 128) == 64 else "pairwise_l1_v2_kernel")
     roofline = {
-        "kernel": "pairwise_l1_v2_kernel", "bound": "fp32", "achieved": achieved, "peak": fp32_peak / 1e12,
+        "kernel": pair_kernel, "bound": "fp32", "achieved": achieved, "peak": fp32_peak / 1e12,
         "unit": "TFLOP/s", "frac": achieved / (fp32_peak / 1e12), "traffic": traffic,
         "peak_source": "measured live: hsd_fp32_peak_probe (register-only FADD sub+|.|-accumulate), "
                        "1 flop per lane per clock; MEASURED_PEAKS.json has no FP32 CUDA-core entry",
@@ -461,8 +463,10 @@ def workload_config(n, hops, world, peer, n_bins):
             "symmetric": world == 1 or peer, "sharded_over_gpus": world,
             "multi_gpu": None if world == 1 else (
                 "BFS kernel stores each signature row into every rank's table over NVLink peer memory "
-                "(fused all-gather, no collective); symmetric tiles dealt round-robin to ranks and mirrored "
-                "into the owners' row blocks through peer memory (torch symmetric memory allocations)" if peer else
+                "(fused all-gather, no collective; from 32k nodes: column-split bitmap recursion + one integer all-reduce "
+                "of the partial counts); every symmetric tile computed once in the job by the owner of its row or "
+                "column block, mirrored store local, direct store into the other owner's row block through NVLink "
+                "peer memory (torch symmetric memory allocations)" if peer else
                 "independent row blocks (every rank computes rows x all columns); one NCCL all-gather")}
 
 

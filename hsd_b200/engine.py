@@ -269,14 +269,16 @@ def signature_from_counts(dg: DeviceGraph, hops: int, counts: torch.Tensor, src:
 def ring_signature_degree(dg: DeviceGraph, hops: int, rows: Optional[torch.Tensor] = None,
                           want_sig: bool = True, want_sizes: bool = True,
                           want_bitmaps: bool = False, empty: str = "raise",
-                          sig_ld: Optional[int] = None):
+                          sig_ld: Optional[int] = None, sig_out: Optional[torch.Tensor] = None):
     """Run the BFS + degree-CDF kernel for the given sources.
 
     rows: int32 CUDA tensor of ORIGINAL node indices (default: all nodes, in
     original order).  Output row r belongs to rows[r].  Returns
     (sig float32[n, sig_ld] | None, ring_sizes int32[n, hops+1] | None,
      bitmaps uint32-as-int32[n, hops+1, n_words] | None, status int32[1]).
-    Bitmaps are indexed by degree-order id (map with dg.orig_of)."""
+    Bitmaps are indexed by degree-order id (map with dg.orig_of).
+    sig_out: a caller-owned float32 CUDA tensor [n, ld >= k_used] (contiguous) that receives the
+    signatures instead of a fresh allocation (DynamicHSD keeps two and swaps them per update)."""
     if empty not in ("raise", "zero"):
         raise ValueError("empty must be 'raise' or 'zero'")
     if empty == "zero" and want_sig and not dg.include_zero:
@@ -292,7 +294,13 @@ def ring_signature_degree(dg: DeviceGraph, hops: int, rows: Optional[torch.Tenso
     out_rows = torch.arange(n_src, dtype=torch.int32, device=dev)
     k_used = dg.k_used(hops)
     ld = int(sig_ld) if sig_ld is not None else roundup(k_used, 4)
-    sig = torch.empty((n_src, ld), dtype=torch.float32, device=dev) if want_sig else None
+    if sig_out is not None:
+        if (not want_sig or sig_out.dtype != torch.float32 or sig_out.dim() != 2 or sig_out.shape[0] != n_src
+                or sig_out.shape[1] < k_used or sig_out.shape[1] % 4 or not sig_out.is_contiguous()):
+            raise ValueError("sig_out must be a contiguous float32 [n_sources, ld >= k_used, ld % 4 == 0] tensor")
+        sig, ld = sig_out, int(sig_out.shape[1])
+    else:
+        sig = torch.empty((n_src, ld), dtype=torch.float32, device=dev) if want_sig else None
     if sig is not None and ld > k_used:
         sig[:, k_used:].zero_()
     sizes = torch.empty((n_src, hops + 1), dtype=torch.int32, device=dev) if want_sizes else None

@@ -31,7 +31,55 @@ from .multiscale_HSD import MultiHSD
 from ._device import on_model_device
 
 
+class _UpdateWorkspace:
+    """Grow-only device buffers of the incremental update, so that a timed update allocates nothing:
+    two signature tables (current / previous, swapped per update), the K-major table
+    [all nodes | one chunk of affected nodes] and the chunk's result block.  The signature length moves with
+    the set of distinct degrees, so the buffers carry slack for 16 more distinct degrees per hop (a fresh
+    cudaMalloc of one 400 MB table costs 30-85 ms on a B200 — more than the ring kernel it feeds;
+    scripts/time_c5_update.py).  Affected rows are recomputed `rows` at a time: bounded memory whatever |A|."""
+
+    def __init__(self, n: int, dev, hops: int, rows: int, k_used: int = 0):
+        self.n, self.dev, self.hops, self.rows = n, dev, hops, rows
+        self.n4 = engine.roundup(n, 4)
+        self._sig = [None, None]
+        self._flip = 0
+        self._sigT = None
+        self.block = torch.empty((rows, self.n4), dtype=torch.float32, device=dev)
+        if k_used > 0:
+            # everything up front, before the N x N matrix exists: a buffer allocated later would be carved out
+            # of a cached free block — after `model._D = None` that is the matrix's own 40 GB block, and the next
+            # matrix then costs a second 40 GB cudaMalloc (measured: 84.7 GB reserved instead of 44.7)
+            self.next_signature_table(n, k_used)
+            self.next_signature_table(n, k_used)
+            self.k_major_table(k_used)
+
+    def _capacity_k(self, k_used: int) -> int:
+        return engine.roundup(k_used + 16 * max(self.hops, 1), engine.PAIR_KCHUNK)
+
+    def next_signature_table(self, n: int, k_used: int) -> torch.Tensor:
+        """float32 [n, roundup(k_used, 4)] view of the buffer that does NOT hold the previous table."""
+        self._flip ^= 1
+        ld = engine.roundup(k_used, 4)
+        buf = self._sig[self._flip]
+        if buf is None or buf.numel() < n * ld:
+            buf = self._sig[self._flip] = torch.empty(n * self._capacity_k(k_used), dtype=torch.float32, device=self.dev)
+        return buf[:n * ld].view(n, ld)
+
+    def k_major_table(self, k_used: int) -> torch.Tensor:
+        """Zeroed float32 [roundup(k_used, 16), n4 + rows] view (the pairwise kernel's TMA source)."""
+        k_pad = engine.roundup(max(k_used, 1), engine.PAIR_KCHUNK)
+        cols = self.n4 + self.rows
+        if self._sigT is None or self._sigT.numel() < k_pad * cols:
+            self._sigT = torch.empty(self._capacity_k(k_used) * cols, dtype=torch.float32, device=self.dev)
+        t = self._sigT[:k_pad * cols].view(k_pad, cols)
+        t.zero_()
+        return t
+
+
 class DynamicHSD(MultiHSD):
+
+    UPDATE_ROWS = 4096       # affected rows recomputed per pairwise launch (bounds the update's workspace)
 
     def __init__(self, graph: nx.Graph, graphName: str, hop: int, n_scales: int, metric="euclidean",
                  signal="wavelet", device=None):
@@ -131,38 +179,49 @@ class DynamicHSD(MultiHSD):
         dg = self._device_graph(include_zero=(self.empty == "zero"))
         n, hops = dg.n, self.hop
         k_used = dg.k_used(hops)
-        sig, _, _, status = engine.ring_signature_degree(dg, hops, empty=self.empty)
+        ws = self._update_workspace(n, k_used, dg.rowptr.device)
+        sig = ws.next_signature_table(n, k_used)
+        _, _, _, status = engine.ring_signature_degree(dg, hops, empty=self.empty, want_sizes=False, sig_out=sig)
         if self.empty == "raise" and int(status.item()) & 1:
             raise engine.EmptyRingError("Distribution can't be empty.")
         prev, prev_support = self._sig_prev, self._support_prev
         self._sig_prev, self._support_prev = sig, dg.support
         same_layout = (self._D is not None and self._D.shape[0] == n and prev is not None
                        and prev.shape == sig.shape and np.array_equal(prev_support, dg.support))
-        if not same_layout:
-            sigT = engine.alloc_signature_table(k_used, n, sig.device)
+        n4 = engine.roundup(n, 4)
+        sigT = ws.k_major_table(k_used)                 # [all nodes | one chunk of affected nodes]
+        if same_layout:
+            aff = torch.nonzero((sig != prev).any(dim=1), as_tuple=False).reshape(-1)   # exact changed set
+            m = int(aff.numel())
+        else:
+            aff, m = torch.arange(n, device=sig.device), n
+        self.last_affected = aff
+        if m * 2 >= n:   # (also: new layout)  rectangular |A| x N costs more than the symmetric full matrix
             engine.signature_transpose(sig, k_used, sigT, 0)
             self._D = engine.pairwise_l1(sigT, n, symmetric=True, k_used=k_used,
                                          out=self._D if self._D is not None and self._D.shape[0] == n else None)
-            self.last_affected = torch.arange(n, device=sig.device)
-            self._pending.clear()
-            return self._D
-        aff = torch.nonzero((sig != prev).any(dim=1), as_tuple=False).reshape(-1)   # exact changed set
-        self.last_affected = aff
-        m = int(aff.numel())
-        if m * 2 >= n:   # rectangular |A| x N costs more than the symmetric full matrix
-            sigT = engine.alloc_signature_table(k_used, n, sig.device)
-            engine.signature_transpose(sig, k_used, sigT, 0)
-            engine.pairwise_l1(sigT, n, symmetric=True, out=self._D, k_used=k_used)
         elif m > 0:
-            # table = [all nodes | affected nodes]; rows = affected block, columns = all nodes
-            n4 = engine.roundup(n, 4)
-            sigT = engine.alloc_signature_table(k_used, n4 + m, sig.device)
+            # rows = a chunk of the affected nodes (appended to the table behind all nodes), columns = all nodes;
+            # hsd_scatter_symmetric writes the chunk's rows and mirrored columns into the resident matrix
             engine.signature_transpose(sig, k_used, sigT, 0)
-            engine.signature_transpose(sig, k_used, sigT, n4, src_rows=aff.to(torch.int32).contiguous())
-            blk = engine.pairwise_l1(sigT, n4 + m, row0=n4, n_rows=m, col0=0, n_cols=n, symmetric=False, k_used=k_used)
-            engine.scatter_symmetric(blk, aff, self._D)       # rows + mirrored columns in one pass over blk
+            rows = ws.rows
+            aff32 = aff.to(torch.int32)
+            for c0 in range(0, m, rows):
+                idx = aff[c0:c0 + rows]
+                mq = int(idx.numel())
+                engine.signature_transpose(sig, k_used, sigT, n4, src_rows=aff32[c0:c0 + rows].contiguous())
+                blk = engine.pairwise_l1(sigT, n4 + rows, row0=n4, n_rows=mq, col0=0, n_cols=n, symmetric=False,
+                                         k_used=k_used, out=ws.block[:mq, :n])
+                engine.scatter_symmetric(blk, idx.contiguous(), self._D)
         self._pending.clear()
         return self._D
+
+    def _update_workspace(self, n: int, k_used: int, dev) -> "_UpdateWorkspace":
+        ws = getattr(self, "_ws", None)
+        if ws is None or ws.n != n or ws.dev != dev:
+            ws = self._ws = _UpdateWorkspace(n, dev, self.hop, min(self.UPDATE_ROWS, engine.roundup(max(n // 2, 4), 4)),
+                                             k_used)
+        return ws
 
     @on_model_device
     def structural_distance_update_sharded(self, rank: int, world: int, group=None, peer: bool = True) -> torch.Tensor:

@@ -21,12 +21,14 @@ def _insertions(g, k, seed=1):
     return sorted(out)
 
 
-@pytest.mark.parametrize("n,k,hop", [(3000, 3, 2), (3000, 30, 3)])
-def test_incremental_equals_from_scratch(n, k, hop):
+@pytest.mark.parametrize("n,k,hop,update_rows", [(3000, 3, 2, None), (3000, 30, 3, None), (3000, 3, 2, 64)])
+def test_incremental_equals_from_scratch(n, k, hop, update_rows):
     import torch
     from model import DynamicHSD, HSD
     g = _ba(n)
     m = DynamicHSD(g.copy(), "ba", hop, 1, "wasserstein", signal="degree")
+    if update_rows:
+        m.UPDATE_ROWS = update_rows       # several chunks of affected rows through the fixed-size workspace
     D0 = m.structural_distance_update().clone()
     new_edges = _insertions(g, k)
     m.dynamic_add_edges(new_edges)
@@ -42,6 +44,10 @@ def test_incremental_equals_from_scratch(n, k, hop):
     mask[aff] = True
     assert not changed[~mask][:, ~mask].any()
     assert 0 < len(aff) <= n
+    if update_rows:
+        assert update_rows < len(aff) < n // 2           # the chunked incremental path, more than one chunk
+    # a second update without an edit changes nothing and recomputes nothing
+    assert torch.equal(m.structural_distance_update(), fresh) and m.last_affected.numel() == 0
     # the exact changed set is inside the analytic bound: nodes within `hop` hops of an endpoint
     m._pending.update(x for e in new_edges for x in e)
     ball = set(m.affected_nodes_device().cpu().numpy().tolist())

@@ -355,3 +355,36 @@ def test_symmetric_tile_list_covers_every_tile_once(n, world, tile_n):
         want = {0} if tile_n == 128 else {h for h in (0, 1) if y * 128 + 64 * h < n}
         assert halves == want
     assert max(counts) <= -(-sum(counts) // world) * 1.03 + 2           # nobody is overloaded (some halves do not exist)
+
+
+def test_dynamic_update_workspace_buffers():
+    """DynamicHSD's grow-only update workspace (host logic, exercised on CPU tensors): the signature tables
+    alternate between two buffers so the previous table survives the next update, a few more distinct degrees
+    fit without a new allocation, and the K-major table comes back zeroed with room for one chunk of rows."""
+    import torch
+    from hsd_b200 import engine
+    from hsd_b200.model.dynamic_HSD import _UpdateWorkspace
+    n, hops, rows = 1001, 3, 64
+    ws = _UpdateWorkspace(n, torch.device("cpu"), hops, rows)
+    a = ws.next_signature_table(n, 436)
+    a.fill_(1.0)
+    b = ws.next_signature_table(n, 436)
+    b.fill_(2.0)
+    assert a.shape == b.shape == (n, 436) and a.is_contiguous() and a.data_ptr() != b.data_ptr()
+    assert float(a.min()) == 1.0                       # the previous table is untouched by the next one
+    c = ws.next_signature_table(n, 436 + 3 * 15)       # 15 more distinct degrees per hop: same buffer as `a`
+    assert c.data_ptr() == a.data_ptr() and c.shape == (n, engine.roundup(436 + 45, 4))
+    assert float(b.min()) == 2.0
+    d = ws.next_signature_table(n, 2000)               # beyond the slack: a new buffer for this slot only
+    assert d.shape == (n, 2000) and d.data_ptr() != b.data_ptr()
+    t = ws.k_major_table(436)
+    assert t.shape == (engine.roundup(436, engine.PAIR_KCHUNK), engine.roundup(n, 4) + rows) and t.is_contiguous()
+    t.fill_(3.0)
+    t2 = ws.k_major_table(440)
+    assert t2.data_ptr() == t.data_ptr() and float(t2.abs().max()) == 0.0
+    assert ws.block.shape == (rows, engine.roundup(n, 4))
+    # allocated up front when the signature length is known: the first updates allocate nothing
+    ws2 = _UpdateWorkspace(n, torch.device("cpu"), hops, rows, k_used=436)
+    ptrs = {ws2._sig[0].data_ptr(), ws2._sig[1].data_ptr()}
+    first, second = ws2.next_signature_table(n, 436), ws2.next_signature_table(n, 440)
+    assert {first.data_ptr(), second.data_ptr()} == ptrs and ws2.k_major_table(436).data_ptr() == ws2._sigT.data_ptr()
